@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""Generate golden parity fixtures by running the UNMODIFIED reference recipe on CPU/gloo.
+
+Test infrastructure only.  Runs in the build container (needs /root/reference, which
+does NOT exist on the GPU box); the .npz files it writes under tests/golden/ are
+committed and are what the -m gpu tests and the oracle tests read.
+
+What is recorded (per config): the initial full state_dict, every micro-batch fed to
+`TrainFinetuneRecipeForNextTokenPrediction._run_train_optim_step`
+(/root/reference/nemo_automodel/recipes/llm/train_ft.py:1482), the returned loss and
+grad_norm of each step, the per-parameter gradients of step 0 as seen by
+`scale_grads_and_clip_grad_norm` (components/training/utils.py:290, i.e. before
+clipping), and the weights after the last step.
+
+Usage:  TORCHDYNAMO_DISABLE=1 python tests/golden/gen_fixtures.py [tiny_fp32|tiny_bf16|tiny_bf16_100|all]
+"""
+import os, sys, types, importlib.machinery, tempfile, json
+
+os.environ.setdefault("TORCHDYNAMO_DISABLE", "1")
+REF = os.environ.get("B200_REFERENCE_PATH", "/root/reference")
+sys.path.insert(0, REF)
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import numpy as np
+import transformers, transformers.utils.import_utils as iu
+from oracle.portable_init import portable_state_dict
+
+iu.is_torchao_available()  # cache False before the stub exists
+
+
+def _mod(name):
+    m = types.ModuleType(name)
+    m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+    m.__path__ = []
+    sys.modules[name] = m
+    return m
+
+
+# ---- stubs for modules the reference imports unconditionally but that are absent here
+ml = _mod("mlflow"); ml.active_run = lambda: None; ml.log_metrics = lambda *a, **k: None
+ta = _mod("torchao"); f8 = _mod("torchao.float8"); f8.precompute_float8_dynamic_scale_for_fsdp = lambda m: None
+q = _mod("torchao.quantization"); qq = _mod("torchao.quantization.qat"); ql = _mod("torchao.quantization.qat.linear")
+
+
+class _Dummy:
+    def __init__(self, *a, **k):
+        pass
+
+
+for n in ["Int4WeightOnlyQATQuantizer", "Int8DynActInt4WeightQATQuantizer", "FakeQuantizeConfig", "IntxFakeQuantizeConfig",
+          "QATConfig", "FromIntXQuantizationAwareTrainingConfig", "IntXQuantizationAwareTrainingConfig"]:
+    setattr(qq, n, _Dummy); setattr(ql, n, _Dummy)
+for n in ["disable_4w_fake_quant", "disable_8da4w_fake_quant", "enable_4w_fake_quant", "enable_8da4w_fake_quant"]:
+    setattr(ql, n, lambda *a, **k: None)
+ta.float8 = f8; ta.quantization = q; q.qat = qq; qq.linear = ql
+fu = _mod("torchao.float8.fsdp_utils")
+
+
+class WeightWithDynamicFloat8CastTensor:
+    pass
+
+
+fu.WeightWithDynamicFloat8CastTensor = WeightWithDynamicFloat8CastTensor; f8.fsdp_utils = fu
+
+import torch
+
+# ---- CPU shims for CUDA-hard-coded call sites (GPU-less host only)
+torch.cuda.reset_peak_memory_stats = lambda *a, **k: None
+torch.cuda.max_memory_allocated = lambda *a, **k: 0
+torch.cuda.empty_cache = lambda *a, **k: None
+torch.cuda.current_device = lambda: 0
+torch.Tensor.cuda = lambda self, *a, **k: self
+
+
+def _fix(d):
+    if isinstance(d, int) and not isinstance(d, bool):
+        return torch.device("cpu")
+    if isinstance(d, torch.device) and d.type == "cuda":
+        return torch.device("cpu")
+    if isinstance(d, str) and d.startswith("cuda"):
+        return torch.device("cpu")
+    return d
+
+
+_to = torch.nn.Module.to
+torch.nn.Module.to = lambda self, *a, **k: _to(self, *tuple(_fix(x) for x in a), **{kk: _fix(v) for kk, v in k.items()})
+_te = torch.nn.Module.to_empty
+torch.nn.Module.to_empty = lambda self, *, device, recurse=True: _te(self, device=_fix(device), recurse=recurse)
+_tt = torch.Tensor.to
+torch.Tensor.to = lambda self, *a, **k: _tt(
+    self, *tuple(x if isinstance(x, (torch.dtype, torch.Tensor)) else _fix(x) for x in a),
+    **{kk: (_fix(v) if kk == "device" else v) for kk, v in k.items()})
+_el = torch.empty_like
+
+
+def _empty_like(t, *a, **k):
+    if "device" in k:
+        k["device"] = _fix(k["device"])
+    return _el(t, *a, **k)
+
+
+torch.empty_like = _empty_like
+
+from nemo_automodel.components.config._arg_parser import parse_args_and_load_config
+import nemo_automodel.recipes.llm.train_ft as train_ft
+from nemo_automodel.recipes.llm.train_ft import TrainFinetuneRecipeForNextTokenPrediction
+
+YAML = """
+recipe: TrainFinetuneRecipeForNextTokenPrediction
+seed: 1234
+step_scheduler: {{global_batch_size: {gbs}, local_batch_size: {lbs}, ckpt_every_steps: 100000, num_epochs: 1, max_steps: {steps}}}
+dist_env: {{backend: gloo, timeout_minutes: 5}}
+model:
+  _target_: nemo_automodel.NeMoAutoModelForCausalLM.from_config
+  config:
+    _target_: transformers.LlamaConfig
+    vocab_size: {vocab}
+    hidden_size: {hidden}
+    intermediate_size: {ffn}
+    num_hidden_layers: {layers}
+    num_attention_heads: {heads}
+    num_key_value_heads: {kv}
+    max_position_embeddings: {seq}
+    rms_norm_eps: 1.0e-5
+    rope_theta: {theta}
+    tie_word_embeddings: false
+    architectures: [LlamaForCausalLM]
+  torch_dtype: {dtype}
+  attn_implementation: sdpa
+  use_liger_kernel: false
+checkpoint: {{enabled: false}}
+distributed: {{strategy: fsdp2, backend: gloo, dp_size: none, tp_size: 1, cp_size: 1}}
+loss_fn: {{_target_: nemo_automodel.components.loss.masked_ce.MaskedCrossEntropy}}
+dataset:
+  _target_: nemo_automodel.components.datasets.llm.mock_iterable_dataset.MockIterableDataset
+  vocab_size: {vocab}
+  seq_len: {seq}
+  num_samples: 100000
+  batch_size: {lbs}
+dataloader: {{_target_: torch.utils.data.DataLoader, batch_size: null}}
+optimizer: {{_target_: torch.optim.AdamW, lr: {lr}, betas: [0.9, 0.95], eps: 1.0e-8, weight_decay: 0.1{opt_extra}}}
+"""
+
+CONFIGS = {
+    # BASELINE.json configs[0]: d_model 256, L 2, seq 512, world 1 (fp32: the exact-math pin for the oracle)
+    "tiny_fp32": dict(gbs=2, lbs=2, steps=3, vocab=1024, hidden=256, ffn=512, layers=2, heads=4, kv=2, seq=512,
+                      theta=10000.0, dtype="float32", lr="1.0e-3", opt_extra=""),
+    # same shapes in bf16 (params, compute and AdamW states bf16 as torch.optim.AdamW does on bf16 params)
+    # 100 steps: the north_star's "step-loss within 1e-3 over 100 steps" curve
+    "tiny_bf16": dict(gbs=2, lbs=2, steps=100, vocab=1024, hidden=256, ffn=512, layers=2, heads=4, kv=2, seq=512,
+                      theta=10000.0, dtype="bfloat16", lr="1.0e-3", opt_extra=""),
+    # head_dim 128 / GQA 4:1 like Llama-3-8B, 2 micro-batches per step (grad accumulation), fp32
+    "hd128_fp32": dict(gbs=2, lbs=1, steps=2, vocab=512, hidden=256, ffn=512, layers=2, heads=2, kv=1, seq=256,
+                       theta=500000.0, dtype="float32", lr="1.0e-3", opt_extra=""),
+}
+
+
+def _np(t):
+    t = t.detach()
+    if hasattr(t, "full_tensor"):
+        t = t.full_tensor()
+    return t.to(torch.float32).cpu().numpy()
+
+
+SEED = 7
+
+
+def _summ(out, prefix, name, a):
+    """Compact per-parameter record: strided sample (<=4096 values) + sum + sum of squares."""
+    flat = a.reshape(-1).astype(np.float64)
+    stride = max(1, flat.size // 4096)
+    out[f"{prefix}/{name}/sample"] = flat[::stride][:4096].astype(np.float32)
+    out[f"{prefix}/{name}/stats"] = np.array([flat.sum(), (flat * flat).sum(), stride], dtype=np.float64)
+
+
+def run(name):
+    c = CONFIGS[name]
+    with tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False) as f:
+        f.write(YAML.format(**c))
+        path = f.name
+    cfg = parse_args_and_load_config(path, argv=[])
+    r = TrainFinetuneRecipeForNextTokenPrediction(cfg)
+    r.setup()
+    model = r.model_parts[0]
+    # ---- both sides start from the same portable snapshot (oracle/portable_init.py)
+    sd = model.state_dict()
+    init = portable_state_dict({k: tuple(v.shape) for k, v in sd.items()}, seed=SEED)
+    with torch.no_grad():
+        for k, v in sd.items():
+            v.copy_(torch.from_numpy(init[k]).to(v.dtype))
+            assert torch.equal(v.float(), torch.from_numpy(init[k])), k   # bf16-representable => exact in both dtypes
+    out = {}
+    rec = {"loss": [], "grad_norm": [], "num_label_tokens": [], "lr": []}
+    step_i = [0]
+    snap_steps = {0, 2, c["steps"] - 1}   # weight summaries after these steps
+
+    orig_clip = train_ft.scale_grads_and_clip_grad_norm
+
+    def clip_spy(max_grad_norm, model_parts, **kw):
+        if step_i[0] == 0:
+            for n, p in model_parts[0].named_parameters():
+                if p.grad is not None:
+                    _summ(out, "grad0", n, _np(p.grad))
+        return orig_clip(max_grad_norm, model_parts, **kw)
+
+    train_ft.scale_grads_and_clip_grad_norm = clip_spy
+    orig_step = r._run_train_optim_step
+
+    def step_spy(batches, max_grad_norm=None):
+        s = step_i[0]
+        for j, b in enumerate(batches):
+            ids = b["input_ids"].numpy()
+            assert ids.max() < 65536
+            out[f"batch/{s}/{j}/input_ids"] = ids.astype(np.uint16)
+            lab = b["labels"].numpy(); pos = b["position_ids"].numpy()
+            # MockIterableDataset (components/datasets/llm/mock_iterable_dataset.py:41-59): labels = shift-left ++ -100
+            assert (lab[:, :-1] == ids[:, 1:]).all() and (lab[:, -1] == -100).all()
+            assert (pos == np.arange(ids.shape[1])[None]).all()
+        m = orig_step(batches, max_grad_norm)
+        rec["loss"].append(float(m.metrics["loss"]))
+        rec["grad_norm"].append(float(m.metrics["grad_norm"]))
+        rec["num_label_tokens"].append(int(m.metrics["num_label_tokens"]))
+        rec["lr"].append(float(m.metrics["lr"]))
+        rec["max_grad_norm"] = max_grad_norm
+        rec["num_micro"] = len(batches)
+        if s in snap_steps:
+            for k, v in model.state_dict().items():
+                _summ(out, f"after{s}", k, _np(v))
+        step_i[0] += 1
+        return m
+
+    r._run_train_optim_step = step_spy
+    r.run_train_validation_loop()
+    opt = r.optimizer[0]
+    out["meta"] = np.frombuffer(json.dumps({
+        "config": c, "init_seed": SEED, "loss": rec["loss"], "grad_norm": rec["grad_norm"],
+        "num_label_tokens": rec["num_label_tokens"], "lr": rec["lr"], "max_grad_norm": rec.get("max_grad_norm"),
+        "num_micro": rec.get("num_micro"), "snap_steps": sorted(snap_steps),
+        "torch": torch.__version__, "transformers": transformers.__version__,
+        "model_class": type(model).__name__, "norm_class": type(model.model.norm).__name__,
+        "optimizer_class": type(opt).__name__,
+        "optimizer": {k: (list(v) if isinstance(v, tuple) else v) for k, v in opt.param_groups[0].items() if k != "params"},
+    }, default=str).encode(), dtype=np.uint8)
+    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), name + ".npz")
+    np.savez_compressed(dst, **out)
+    print(name, "loss", rec["loss"][:3], "grad_norm", rec["grad_norm"][:3], "->", dst, os.path.getsize(dst) // 1024, "KiB")
+    train_ft.scale_grads_and_clip_grad_norm = orig_clip
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    names = list(CONFIGS) if which == "all" else [which]
+    # one recipe per process (the reference initialises a process group in setup())
+    if len(names) > 1:
+        import subprocess
+        for n in names:
+            subprocess.check_call([sys.executable, __file__, n])
+    else:
+        run(names[0])
