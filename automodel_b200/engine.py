@@ -1,0 +1,453 @@
+"""Sharded-data-parallel Llama training step on B200: host orchestration over the sm_100a kernels.
+
+This is the replacement for what the reference's `_forward_backward_step` / `_run_train_optim_step`
+(/root/reference/nemo_automodel/recipes/llm/train_ft.py:1357-1473, 1482-1635) reach through
+torch FSDP2 + DTensor + ATen/cuBLAS/flash-attn:
+
+  per-unit parameter all-gather  ->  transformer-block forward/backward  ->  gradient reduce-scatter
+  ->  grad-norm + clip  ->  AdamW on the local shard.
+
+Design (B200-first, 180 GB HBM per GPU):
+  * flat bf16 storage per unit (layout.py); a rank's parameter shard is a slice *inside* the unsharded buffer, so the
+    all-gather is in place and happens ONCE per optimizer step (parameters stay gathered through forward and backward:
+    16 GB for Llama-3-8B), halving the reference's all-gather traffic (it re-gathers every layer in backward,
+    parallelizer.py:860-871);
+  * gradients are produced by the wgrad GEMMs directly into the unit's flat gradient buffer; the reduce-scatter is in
+    place on that buffer and overlaps the backward of the next unit on a side stream;
+  * explicit forward/backward over pre-allocated activation arenas - no autograd graph, no caching-allocator churn;
+  * grad-norm is one fused reduction per unit + one scalar all-reduce; the clip coefficient never visits the host.
+All device math is in csrc/ (via ops); torch provides memory, streams and torch.distributed only.
+"""
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .layout import LlamaDims, UnitLayout, build_layout, total_params
+
+IGNORE_INDEX = -100
+
+
+def _rope_inv_freq(d: LlamaDims) -> torch.Tensor:
+    """inv_freq as the reference computes it (components/models/llama/rope_utils.py:108-150), fp32 on the host."""
+    D = d.head_dim
+    inv = 1.0 / (torch.tensor(float(d.rope_theta), dtype=torch.float32) ** (torch.arange(0, D, 2, dtype=torch.int64).float() / D))
+    sc = d.rope_scaling or {}
+    rtype = sc.get("rope_type", sc.get("type", "default"))
+    if rtype == "default":
+        return inv
+    factor = sc.get("factor", 1.0)
+    lo, hi = sc.get("low_freq_factor", 1.0), sc.get("high_freq_factor", 4.0)
+    old = sc.get("original_max_position_embeddings", d.max_pos)
+    low_wl, high_wl = old / lo, old / hi
+    wavelen = 2 * math.pi / inv
+    inv_l = torch.where(wavelen > low_wl, inv / factor, inv)
+    smooth = (old / wavelen - lo) / (hi - lo)
+    smoothed = (1 - smooth) * inv_l / factor + smooth * inv_l
+    med = (~(wavelen < high_wl)) & (~(wavelen > low_wl))
+    return torch.where(med, smoothed, inv_l)
+
+
+def rope_tables(d: LlamaDims, n_pos: int, device) -> (torch.Tensor, torch.Tensor):
+    """bf16 cos/sin tables [n_pos, head_dim] (rope_utils.py:191-205: fp32 math, rounded to the model dtype)."""
+    inv = _rope_inv_freq(d)
+    t = torch.arange(n_pos, dtype=torch.float32)
+    freqs = torch.outer(t, inv)
+    emb = torch.cat((freqs, freqs), dim=-1)
+    return emb.cos().to(torch.bfloat16).to(device), emb.sin().to(torch.bfloat16).to(device)
+
+
+def cu_seqlens_from_position_ids(position_ids: np.ndarray):
+    """Packed batches restart position_ids at every document (components/datasets/llm/packed_sequence.py:37-110).
+    position_ids [b,S] (host) -> (cu_seqlens int32 [nseq+1] over the flattened b*S tokens, max_seqlen)."""
+    b, S = position_ids.shape
+    flat = position_ids.reshape(-1)
+    starts = np.flatnonzero(flat == 0)
+    row_starts = np.arange(b) * S
+    starts = np.union1d(starts, row_starts)
+    cu = np.concatenate([starts, [b * S]]).astype(np.int32)
+    return cu, int(np.diff(cu).max())
+
+
+class _Streams:
+    """CUDA streams/events; no-ops on CPU (CPU execution exists only for the orchestration tests)."""
+
+    def __init__(self, device):
+        self.cuda = device.type == "cuda"
+        self.comm = torch.cuda.Stream(device) if self.cuda else None
+
+    def event(self):
+        return torch.cuda.Event() if self.cuda else None
+
+    def record(self, ev, stream=None):
+        if self.cuda:
+            ev.record(stream if stream is not None else torch.cuda.current_stream())
+
+    def wait(self, ev, stream=None):
+        if self.cuda and ev is not None:
+            (stream if stream is not None else torch.cuda.current_stream()).wait_event(ev)
+
+
+class ShardedLlamaEngine:
+    """One rank of the sharded-DP training step.  `ops` is automodel_b200.ops (CUDA); tests inject a CPU stand-in to
+    exercise the orchestration over gloo without a GPU."""
+
+    def __init__(self, cfg, device, process_group=None, max_tokens=4096, lr=1e-5, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1,
+                 adam_mode=0, master_weights=False, ops=None, max_positions=None, reference_rounding=True):
+        if ops is None:
+            from . import ops as _ops  # raises if libb200_train.so is missing: no fallback
+            ops = _ops
+        self.ops = ops
+        self.dims = cfg if isinstance(cfg, LlamaDims) else LlamaDims.from_hf(cfg)
+        d = self.dims
+        self.device = torch.device(device)
+        self.pg = process_group
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+            self.rank = dist.get_rank(process_group)
+        else:
+            self.world, self.rank = 1, 0
+        self.units: List[UnitLayout] = build_layout(d, self.world)
+        self.n_params = total_params(self.units)
+        self.max_tokens = max_tokens
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.adam_mode = adam_mode
+        self.round_before_add = bool(reference_rounding)
+        self.step_count = 0
+        self.streams = _Streams(self.device)
+        bf, dev = torch.bfloat16, self.device
+
+        # ---- persistent flat storage
+        self.p_full = [torch.zeros(u.padded, dtype=bf, device=dev) for u in self.units]   # unsharded params (shard lives inside)
+        self.g_full = [torch.zeros(u.padded, dtype=bf, device=dev) for u in self.units]   # unsharded grads (RS in place)
+        self.m = [torch.zeros(u.padded // self.world, dtype=bf, device=dev) for u in self.units]
+        self.v = [torch.zeros(u.padded // self.world, dtype=bf, device=dev) for u in self.units]
+        self.master = [torch.zeros(u.padded // self.world, dtype=torch.float32, device=dev) for u in self.units] if master_weights else None
+        self.P: Dict[str, torch.Tensor] = {}
+        self.G: Dict[str, torch.Tensor] = {}
+        for ui, u in enumerate(self.units):
+            for s in u.slots:
+                self.P[s.name] = self.p_full[ui][s.offset:s.offset + s.numel].view(s.shape)
+                self.G[s.name] = self.g_full[ui][s.offset:s.offset + s.numel].view(s.shape)
+        self._mk_fused_views()
+        self.ev_ag = [None] * len(self.units)   # all-gather of unit done
+        self.ev_rs = [None] * len(self.units)   # reduce-scatter of unit done
+
+        n_pos = max_positions or max(d.max_pos, 1)
+        self.cos, self.sin = rope_tables(d, n_pos, dev)
+
+        # ---- activation arenas (allocated once for max_tokens)
+        T, h, F, L = max_tokens, d.hidden, d.ffn, d.layers
+        e = lambda *shape, dtype=bf: torch.empty(*shape, dtype=dtype, device=dev)
+        self.act = {
+            "h": [e(T, h) for _ in range(L + 1)],            # residual stream: h[l] = input of layer l, h[L] = output
+            "x1": [e(T, h) for _ in range(L)],
+            "rstd1": [e(T, dtype=torch.float32) for _ in range(L)],
+            "qkv": [e(T, d.qkv_cols) for _ in range(L)],
+            "lse": [e(d.heads, T, dtype=torch.float32) for _ in range(L)],
+            "o2": [e(T, d.q_cols) for _ in range(L)],
+            "h1": [e(T, h) for _ in range(L)],
+            "x2": [e(T, h) for _ in range(L)],
+            "rstd2": [e(T, dtype=torch.float32) for _ in range(L)],
+            "gu": [e(T, 2 * F) for _ in range(L)],
+            "a": [e(T, F) for _ in range(L)],
+        }
+        self.xf, self.rstdf = e(T, h), e(T, dtype=torch.float32)
+        self.logits = e(T, d.vocab)
+        self.row_loss = e(T, dtype=torch.float32)
+        self.tmp = {
+            "dh_a": e(T, h), "dh_b": e(T, h), "dxf": e(T, h), "da": e(T, F), "dgu": e(T, 2 * F), "dx": e(T, h),
+            "do2": e(T, d.q_cols), "dqkv": e(T, d.qkv_cols),
+        }
+        # token inputs: two (pinned host, device) buffer sets used alternately, so the host can stage micro-batch i+1 while
+        # the device still reads micro-batch i (embed_bwd at the very end of backward needs the ids)
+        pin = self.device.type == "cuda"
+        self._in_dev = [torch.empty(4 * T + 1, dtype=torch.int32, device=dev) for _ in range(2)]   # ids | labels | pos | cu
+        self._in_host = [torch.empty(4 * T + 1, dtype=torch.int32, pin_memory=pin) for _ in range(2)]
+        self._in_ev = [None, None]
+        self._in_idx = 0
+        self.h2d_bytes = 0
+        self.embed_ws = torch.empty(2 * T, dtype=torch.int32, device=dev)
+        if self.device.type == "cuda":
+            from ._lib import lib
+            self.norm_ws = torch.empty(lib().b200_rmsnorm_bwd_workspace_floats(T, h), dtype=torch.float32, device=dev)
+            self.attn_ws = torch.empty(lib().b200_attn_bwd_workspace_bytes(T, d.heads, d.head_dim), dtype=torch.uint8, device=dev)
+        else:
+            self.norm_ws = self.attn_ws = None
+        self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.norm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._grads_dirty = False
+
+    # ------------------------------------------------------------------ parameter plumbing
+    def _mk_fused_views(self):
+        d = self.dims
+        self.W = []
+        for l in range(d.layers):
+            ui = 1 + l
+            u = self.units[ui]
+            off = {s.name.split(".", 3)[3]: s.offset for s in u.slots}
+            pf, gf = self.p_full[ui], self.g_full[ui]
+
+            def view(buf, o, r, c):
+                return buf[o:o + r * c].view(r, c)
+
+            self.W.append({
+                "qkv": view(pf, off["self_attn.q_proj.weight"], d.qkv_cols, d.hidden),
+                "o": view(pf, off["self_attn.o_proj.weight"], d.hidden, d.q_cols),
+                "gu": view(pf, off["mlp.gate_proj.weight"], 2 * d.ffn, d.hidden),
+                "down": view(pf, off["mlp.down_proj.weight"], d.hidden, d.ffn),
+                "n1": pf[off["input_layernorm.weight"]:off["input_layernorm.weight"] + d.hidden],
+                "n2": pf[off["post_attention_layernorm.weight"]:off["post_attention_layernorm.weight"] + d.hidden],
+                "d_qkv": view(gf, off["self_attn.q_proj.weight"], d.qkv_cols, d.hidden),
+                "d_o": view(gf, off["self_attn.o_proj.weight"], d.hidden, d.q_cols),
+                "d_gu": view(gf, off["mlp.gate_proj.weight"], 2 * d.ffn, d.hidden),
+                "d_down": view(gf, off["mlp.down_proj.weight"], d.hidden, d.ffn),
+                "d_n1": gf[off["input_layernorm.weight"]:off["input_layernorm.weight"] + d.hidden],
+                "d_n2": gf[off["post_attention_layernorm.weight"]:off["post_attention_layernorm.weight"] + d.hidden],
+            })
+
+    def load_state_dict(self, sd):
+        """sd: HF-named full tensors (torch or numpy, any float dtype).  Every rank loads the full model (the metric's
+        random-init / a from_pretrained snapshot); optimizer shards start at zero."""
+        with torch.no_grad():
+            for name, dst in self.P.items():
+                src = sd[name]
+                if isinstance(src, np.ndarray):
+                    src = torch.from_numpy(np.ascontiguousarray(src))
+                dst.copy_(src.to(dst.dtype).reshape(dst.shape))
+            if self.master is not None:
+                for ui, u in enumerate(self.units):
+                    a, b = u.shard_range(self.rank, self.world)
+                    self.master[ui].copy_(self.p_full[ui][a:b].float())
+        for t in self.m + self.v:
+            t.zero_()
+        self.step_count = 0
+
+    def init_random_(self, seed=0, std=0.02):
+        """Random init of the metric config, on device: N(0, std) linears/embeddings, ones for norms
+        (HF initialize_weights semantics, components/checkpoint/checkpointing.py:574-676).  Same values on every rank."""
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        with torch.no_grad():
+            for name, p in self.P.items():
+                if name.endswith("norm.weight") or "layernorm" in name:
+                    p.fill_(1.0)
+                else:
+                    p.copy_((torch.randn(p.shape, generator=g, device=self.device, dtype=torch.float32) * std).to(p.dtype))
+        self.load_state_dict(self.P)
+
+    def state_dict(self):
+        return dict(self.P)
+
+    def named_grads(self):
+        return dict(self.G)
+
+    def shard(self, bufs, ui):
+        a, b = self.units[ui].shard_range(self.rank, self.world)
+        return bufs[ui][a:b]
+
+    # ------------------------------------------------------------------ collectives (NCCL over NVLink via torch.distributed)
+    def _all_gather_unit(self, ui):
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        st = self.streams
+        ev = st.event()
+        st.record(ev)                       # shard update (AdamW) issued on the compute stream
+        if st.cuda:
+            with torch.cuda.stream(st.comm):
+                st.wait(ev, st.comm)
+                dist.all_gather_into_tensor(self.p_full[ui], self.shard(self.p_full, ui), group=self.pg)
+                done = st.event()
+                st.record(done, st.comm)
+                self.ev_ag[ui] = done
+        else:
+            dist.all_gather_into_tensor(self.p_full[ui], self.shard(self.p_full, ui).clone(), group=self.pg)
+
+    def _reduce_scatter_unit(self, ui):
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        st = self.streams
+        ev = st.event()
+        st.record(ev)                       # this unit's gradients are complete on the compute stream
+        if st.cuda:
+            with torch.cuda.stream(st.comm):
+                st.wait(ev, st.comm)
+                dist.reduce_scatter_tensor(self.shard(self.g_full, ui), self.g_full[ui], op=dist.ReduceOp.SUM, group=self.pg)
+                done = st.event()
+                st.record(done, st.comm)
+                self.ev_rs[ui] = done
+        else:
+            out = torch.empty_like(self.shard(self.g_full, ui))
+            dist.reduce_scatter_tensor(out, self.g_full[ui].clone(), op=dist.ReduceOp.SUM, group=self.pg)
+            self.shard(self.g_full, ui).copy_(out)
+
+    def _wait_params(self, ui):
+        if self.ev_ag[ui] is not None:
+            self.streams.wait(self.ev_ag[ui])
+            self.ev_ag[ui] = None
+
+    # ------------------------------------------------------------------ forward + backward of one micro-batch
+    def _stage_inputs(self, input_ids, labels, position_ids):
+        """Host int64 [b,S] tensors -> pinned int32 staging -> ONE async H2D copy of [ids | labels | pos | cu_seqlens]."""
+        b, S = input_ids.shape
+        T = b * S
+        if T > self.max_tokens:
+            raise ValueError(f"micro-batch of {T} tokens exceeds max_tokens={self.max_tokens}")
+        if position_ids is None:
+            pos_np = np.ascontiguousarray(np.broadcast_to(np.arange(S, dtype=np.int64), (b, S)))
+        else:
+            pos_np = position_ids.cpu().numpy()
+        cu_np, max_len = cu_seqlens_from_position_ids(pos_np)
+        nseq = cu_np.size - 1
+        k = self._in_idx
+        self._in_idx ^= 1
+        if self._in_ev[k] is not None:
+            self._in_ev[k].synchronize()      # the copy that last used this pinned buffer has completed
+        host, devb = self._in_host[k], self._in_dev[k]
+        host[0:T].copy_(input_ids.reshape(-1))
+        host[T:2 * T].copy_(labels.reshape(-1))
+        host[2 * T:3 * T].copy_(torch.from_numpy(pos_np).reshape(-1))
+        host[3 * T:3 * T + nseq + 1].copy_(torch.from_numpy(cu_np))
+        n = 3 * T + nseq + 1
+        devb[:n].copy_(host[:n], non_blocking=True)
+        self.h2d_bytes += n * 4
+        if self.streams.cuda:
+            ev = self.streams.event()
+            self.streams.record(ev)
+            self._in_ev[k] = ev
+        self.ids, self.labels, self.pos = devb[0:T], devb[T:2 * T], devb[2 * T:3 * T]
+        self.cu = devb[3 * T:3 * T + nseq + 1]
+        return T, nseq, max_len
+
+    def forward_backward(self, input_ids, labels, position_ids, num_label_tokens, first_micro=True, last_micro=True):
+        """One micro-batch.  Loss (already divided by the GLOBAL label-token count, train_ft.py:1449-1473) accumulates in
+        self.loss_dev; parameter gradients (= or +=) land in the flat gradient buffers; on the last micro-batch each unit's
+        gradients are reduce-scattered as soon as its backward is done."""
+        ops, d, A, tmp = self.ops, self.dims, self.act, self.tmp
+        T, nseq, max_len = self._stage_inputs(input_ids, labels, position_ids)
+        ids, lab, pos, cu = self.ids, self.labels, self.pos, self.cu
+        L, Hq, Hkv, D = d.layers, d.heads, d.kv_heads, d.head_dim
+        qc, kc = d.q_cols, d.kv_cols
+        rba = self.round_before_add
+        acc = not first_micro
+        sl = lambda t: t[:T]
+
+        # ---------------- forward (models/llama/model.py:293-388, 203-234)
+        self._wait_params(0)
+        ops.embed_fwd(ids, self.P["model.embed_tokens.weight"], out=sl(A["h"][0]))
+        for l in range(L):
+            self._wait_params(1 + l)
+            W = self.W[l]
+            h = sl(A["h"][l])
+            x1 = sl(A["x1"][l]); qkv = sl(A["qkv"][l]); o2 = sl(A["o2"][l]); h1 = sl(A["h1"][l])
+            x2 = sl(A["x2"][l]); gu = sl(A["gu"][l]); a = sl(A["a"][l])
+            ops.rmsnorm_fwd(h, W["n1"], d.eps, out=x1, rstd=sl(A["rstd1"][l]))
+            ops.gemm(ops.NT, x1, W["qkv"], out=qkv)
+            ops.rope_(qkv, self.cos, self.sin, pos, Hq + Hkv, D)
+            ops.attn_fwd(qkv[:, :qc], qkv[:, qc:qc + kc], qkv[:, qc + kc:], cu, max_len, Hq, Hkv, D, out=o2, lse=A["lse"][l])
+            ops.gemm(ops.NT, o2, W["o"], out=h1, residual=h, round_before_add=rba)
+            ops.rmsnorm_fwd(h1, W["n2"], d.eps, out=x2, rstd=sl(A["rstd2"][l]))
+            ops.gemm(ops.NT, x2, W["gu"], out=gu)
+            ops.swiglu_fwd(gu, out=a)
+            ops.gemm(ops.NT, a, W["down"], out=sl(A["h"][l + 1]), residual=h1, round_before_add=rba)
+        self._wait_params(1 + L)
+        hL = sl(A["h"][L])
+        xf = sl(self.xf)
+        ops.rmsnorm_fwd(hL, self.P["model.norm.weight"], d.eps, out=xf, rstd=sl(self.rstdf))
+        logits = sl(self.logits)
+        ops.gemm(ops.NT, xf, self.P["lm_head.weight"], out=logits)
+        # fused CE: loss accumulates on the device, logits become dlogits in place (components/loss/masked_ce.py:73-89)
+        ops.ce_fwd_bwd_(logits, lab, num_label_tokens, self.loss_dev, accumulate=True, row_loss=sl(self.row_loss))
+
+        # ---------------- backward
+        head_ui = 1 + L
+        ops.gemm(ops.TN, logits, xf, out=self.G["lm_head.weight"], residual=self.G["lm_head.weight"] if acc else None)
+        dxf = sl(tmp["dxf"])
+        ops.gemm(ops.NN, logits, self.P["lm_head.weight"], out=dxf)
+        dh = sl(tmp["dh_a"]); dh_next = sl(tmp["dh_b"])
+        ops.rmsnorm_bwd(dxf, hL, self.P["model.norm.weight"], sl(self.rstdf), dx=dh, dw=self.G["model.norm.weight"],
+                        accumulate_dw=acc, workspace=self.norm_ws)
+        if last_micro:
+            self._reduce_scatter_unit(head_ui)
+        for l in reversed(range(L)):
+            W = self.W[l]
+            h = sl(A["h"][l]); x1 = sl(A["x1"][l]); qkv = sl(A["qkv"][l]); o2 = sl(A["o2"][l]); h1 = sl(A["h1"][l])
+            x2 = sl(A["x2"][l]); gu = sl(A["gu"][l]); a = sl(A["a"][l])
+            da = sl(tmp["da"]); dgu = sl(tmp["dgu"]); dx = sl(tmp["dx"]); do2 = sl(tmp["do2"]); dqkv = sl(tmp["dqkv"])
+            # MLP
+            ops.gemm(ops.TN, dh, a, out=W["d_down"], residual=W["d_down"] if acc else None)
+            ops.gemm(ops.NN, dh, W["down"], out=da)
+            ops.swiglu_bwd(da, gu, out=dgu)
+            ops.gemm(ops.TN, dgu, x2, out=W["d_gu"], residual=W["d_gu"] if acc else None)
+            ops.gemm(ops.NN, dgu, W["gu"], out=dx)
+            # dh1 = dh + rmsnorm'(dx2)
+            ops.rmsnorm_bwd(dx, h1, W["n2"], sl(A["rstd2"][l]), dres=dh, dx=dh_next, dw=W["d_n2"], accumulate_dw=acc, workspace=self.norm_ws)
+            dh, dh_next = dh_next, dh
+            # attention
+            ops.gemm(ops.TN, dh, o2, out=W["d_o"], residual=W["d_o"] if acc else None)
+            ops.gemm(ops.NN, dh, W["o"], out=do2)
+            ops.attn_bwd(qkv[:, :qc], qkv[:, qc:qc + kc], qkv[:, qc + kc:], o2, do2, A["lse"][l], cu, max_len, Hq, Hkv, D,
+                         dqkv[:, :qc], dqkv[:, qc:qc + kc], dqkv[:, qc + kc:], workspace=self.attn_ws)
+            ops.rope_(dqkv, self.cos, self.sin, pos, Hq + Hkv, D, backward=True)
+            ops.gemm(ops.TN, dqkv, x1, out=W["d_qkv"], residual=W["d_qkv"] if acc else None)
+            ops.gemm(ops.NN, dqkv, W["qkv"], out=dx)
+            ops.rmsnorm_bwd(dx, h, W["n1"], sl(A["rstd1"][l]), dres=dh, dx=dh_next, dw=W["d_n1"], accumulate_dw=acc, workspace=self.norm_ws)
+            dh, dh_next = dh_next, dh
+            if last_micro:
+                self._reduce_scatter_unit(1 + l)
+        if first_micro:
+            self.G["model.embed_tokens.weight"].zero_()
+        ops.embed_bwd(ids, dh, self.G["model.embed_tokens.weight"], accumulate=True, workspace=self.embed_ws)
+        if last_micro:
+            self._reduce_scatter_unit(0)
+        self._grads_dirty = True
+
+    # ------------------------------------------------------------------ grad-norm, clip, AdamW, parameter all-gather
+    def optimizer_step(self, max_grad_norm: Optional[float] = 1.0, lr: Optional[float] = None):
+        """components/training/utils.py:65-171 + train_ft.py:1556-1558 on the flat shards.  Returns the device scalar
+        holding the squared global grad norm (sqrt on the host only for logging)."""
+        ops = self.ops
+        if lr is not None:
+            self.lr = lr
+        self.step_count += 1
+        nu = len(self.units)
+        for ui in range(nu):
+            if self.ev_rs[ui] is not None:
+                self.streams.wait(self.ev_rs[ui])
+                self.ev_rs[ui] = None
+            ops.sumsq_(self.shard(self.g_full, ui), self.norm_sq, accumulate=ui > 0)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.norm_sq, op=dist.ReduceOp.SUM, group=self.pg)
+        for ui in range(nu):
+            ops.adamw_step_(self.shard(self.p_full, ui), self.shard(self.g_full, ui), self.m[ui], self.v[ui], self.lr, self.betas[0],
+                            self.betas[1], self.eps, self.wd, self.step_count, max_grad_norm=max_grad_norm or 0.0,
+                            grad_norm_sq=self.norm_sq, mode=self.adam_mode, master=None if self.master is None else self.master[ui])
+            self._all_gather_unit(ui)
+        self._grads_dirty = False
+        return self.norm_sq
+
+    def train_step(self, micro_batches, max_grad_norm: Optional[float] = 1.0, num_label_tokens: Optional[int] = None):
+        """micro_batches: list of dicts with host tensors input_ids / labels [/ position_ids] of shape [b,S].
+        Returns (loss, grad_norm) as 0-d device tensors (no host sync here)."""
+        if num_label_tokens is None:
+            n = sum(int((mb["labels"] != IGNORE_INDEX).sum()) for mb in micro_batches)
+            if self.world > 1:
+                import torch.distributed as dist
+                t = torch.tensor([n], dtype=torch.int64, device=self.device)
+                dist.all_reduce(t, group=self.pg)
+                n = int(t.item())
+            num_label_tokens = n
+        self.loss_dev.zero_()
+        for i, mb in enumerate(micro_batches):
+            self.forward_backward(mb["input_ids"], mb["labels"], mb.get("position_ids"), num_label_tokens,
+                                  first_micro=(i == 0), last_micro=(i == len(micro_batches) - 1))
+        nsq = self.optimizer_step(max_grad_norm)
+        loss = self.loss_dev.clone()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.pg)
+        return loss[0], nsq.sqrt()[0]

@@ -1,0 +1,121 @@
+"""Flat sharded parameter layout of the B200 sharded-DP step.
+
+Replaces the reference's per-parameter DTensor Shard(0) plan
+(/root/reference/nemo_automodel/components/distributed/parallelizer.py:137-319, 791-903: one FSDP unit per decoder
+layer + a root unit) with contiguous flat bf16 buffers: one per unit, each rank owning the contiguous 1/N slice
+[rank*n/N, (rank+1)*n/N).  No padding per parameter, one collective per unit, no copy-in/copy-out: the all-gather
+output *is* the unsharded parameter storage and the reduce-scatter input *is* the gradient storage.
+Inside a unit the HF parameters are laid out so that fused contractions see one matrix:
+    [q_proj; k_proj; v_proj] -> one [(Hq+2Hkv)*d, h] weight,   [gate_proj; up_proj] -> one [2F, h] weight.
+HF names/shapes (models/llama/model.py:85-101,162-166) are preserved as views for state_dict / checkpoint export.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Tuple
+
+ALIGN = 8  # elements: 16-byte vector / TMA base alignment for bf16
+
+
+@dataclass
+class LlamaDims:
+    hidden: int
+    ffn: int
+    layers: int
+    heads: int
+    kv_heads: int
+    head_dim: int
+    vocab: int
+    eps: float = 1e-5
+    rope_theta: float = 10000.0
+    rope_scaling: dict = None
+    max_pos: int = 4096
+
+    @staticmethod
+    def from_hf(cfg) -> "LlamaDims":
+        g = (lambda k, d=None: cfg.get(k, d)) if isinstance(cfg, dict) else (lambda k, d=None: getattr(cfg, k, d))
+        heads = g("num_attention_heads")
+        hidden = g("hidden_size")
+        if g("tie_word_embeddings", False):
+            raise ValueError("tie_word_embeddings=True is not supported by the B200 flat layout (Llama-3 is untied)")
+        if g("attention_bias", False) or g("mlp_bias", False):
+            raise ValueError("attention_bias / mlp_bias are not supported")
+        return LlamaDims(hidden=hidden, ffn=g("intermediate_size"), layers=g("num_hidden_layers"), heads=heads,
+                         kv_heads=g("num_key_value_heads") or heads, head_dim=g("head_dim") or hidden // heads,
+                         vocab=g("vocab_size"), eps=g("rms_norm_eps", 1e-5), rope_theta=g("rope_theta", 10000.0) or 10000.0,
+                         rope_scaling=g("rope_scaling"), max_pos=g("max_position_embeddings", 4096))
+
+    @property
+    def q_cols(self):
+        return self.heads * self.head_dim
+
+    @property
+    def kv_cols(self):
+        return self.kv_heads * self.head_dim
+
+    @property
+    def qkv_cols(self):
+        return self.q_cols + 2 * self.kv_cols
+
+
+@dataclass
+class ParamSlot:
+    name: str           # HF name
+    shape: Tuple[int, ...]
+    offset: int         # element offset inside the unit's flat buffer
+
+    @property
+    def numel(self):
+        n = 1
+        for s in self.shape:
+            n *= s
+        return n
+
+
+@dataclass
+class UnitLayout:
+    name: str
+    slots: List[ParamSlot] = field(default_factory=list)
+    numel: int = 0        # un-padded
+    padded: int = 0       # multiple of world*ALIGN
+
+    def shard_range(self, rank: int, world: int) -> Tuple[int, int]:
+        per = self.padded // world
+        return rank * per, (rank + 1) * per
+
+
+def _mk_unit(name: str, entries: List[Tuple[str, Tuple[int, ...]]], world: int) -> UnitLayout:
+    u = UnitLayout(name)
+    off = 0
+    for pname, shape in entries:
+        slot = ParamSlot(pname, tuple(shape), off)
+        if slot.numel % ALIGN:
+            raise ValueError(f"{pname}: numel {slot.numel} is not a multiple of {ALIGN}")
+        u.slots.append(slot)
+        off += slot.numel
+    u.numel = off
+    q = world * ALIGN
+    u.padded = (off + q - 1) // q * q
+    return u
+
+
+def build_layout(d: LlamaDims, world: int) -> List[UnitLayout]:
+    """Units in forward order: embed, layer 0..L-1, head (final norm + lm_head)."""
+    units = [_mk_unit("embed", [("model.embed_tokens.weight", (d.vocab, d.hidden))], world)]
+    for l in range(d.layers):
+        p = f"model.layers.{l}."
+        units.append(_mk_unit(f"layer{l}", [
+            (p + "self_attn.q_proj.weight", (d.q_cols, d.hidden)),
+            (p + "self_attn.k_proj.weight", (d.kv_cols, d.hidden)),
+            (p + "self_attn.v_proj.weight", (d.kv_cols, d.hidden)),
+            (p + "self_attn.o_proj.weight", (d.hidden, d.q_cols)),
+            (p + "mlp.gate_proj.weight", (d.ffn, d.hidden)),
+            (p + "mlp.up_proj.weight", (d.ffn, d.hidden)),
+            (p + "mlp.down_proj.weight", (d.hidden, d.ffn)),
+            (p + "input_layernorm.weight", (d.hidden,)),
+            (p + "post_attention_layernorm.weight", (d.hidden,)),
+        ], world))
+    units.append(_mk_unit("head", [("model.norm.weight", (d.hidden,)), ("lm_head.weight", (d.vocab, d.hidden))], world))
+    return units
+
+
+def total_params(units: List[UnitLayout]) -> int:
+    return sum(u.numel for u in units)

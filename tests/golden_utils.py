@@ -54,3 +54,19 @@ def check_summary(z, prefix, name, arr, rtol, atol, outlier_frac=0.0, outlier_at
     ref_l2 = np.sqrt(stats[1]); got_l2 = np.sqrt((flat * flat).sum())
     assert abs(got_l2 - ref_l2) <= rtol * ref_l2 + atol * np.sqrt(flat.size), f"{prefix}/{name} l2 {got_l2} vs {ref_l2}"
     return np.abs(got - ref).max()
+
+
+def check_rel_l2(z, prefix, name, arr, tol):
+    """Relative L2 error of the strided sample and of the full-tensor norm (for bf16 gradients, where per-element
+    tolerances are meaningless on sparse / near-zero rows)."""
+    flat = np.asarray(arr, dtype=np.float64).reshape(-1)
+    stats = z[f"{prefix}/{name}/stats"]
+    stride = int(stats[2])
+    ref = z[f"{prefix}/{name}/sample"].astype(np.float64)
+    got = flat[::stride][:4096]
+    den = max(np.linalg.norm(ref), 1e-12)
+    rel = np.linalg.norm(got - ref) / den
+    assert rel <= tol, f"{prefix}/{name}: sample rel-l2 {rel:.4f} > {tol}"
+    ref_l2 = np.sqrt(stats[1]); got_l2 = np.sqrt((flat * flat).sum())
+    assert abs(got_l2 - ref_l2) <= tol * ref_l2 + 1e-12, f"{prefix}/{name}: l2 {got_l2} vs {ref_l2}"
+    return rel

@@ -1,0 +1,131 @@
+"""Host-side orchestration of the sharded step, exercised on CPU with the torch stand-in kernels (tests/cpu_kernels.py):
+flat layout and fused-weight views, accumulate flags, grad-norm/clip/AdamW plumbing, and - over gloo, world size 2 - the
+in-place reduce-scatter / all-gather schedule.  Parity targets: the reference-generated fixtures and the numpy oracle."""
+import os
+import sys
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from automodel_b200.engine import ShardedLlamaEngine, cu_seqlens_from_position_ids
+from automodel_b200.layout import LlamaDims, build_layout, total_params
+from tests import cpu_kernels
+from tests.golden_utils import load, model_cfg, init_params, batches, check_summary, check_rel_l2
+
+
+def _mb(b):
+    return {"input_ids": torch.from_numpy(b["input_ids"]), "labels": torch.from_numpy(b["labels"])}
+
+
+def test_layout_matches_survey_constants():
+    """Llama-3-8B = 8,030,261,248 params, 218,112,000 per layer; tiny = 1,705,216."""
+    d = LlamaDims(hidden=4096, ffn=14336, layers=32, heads=32, kv_heads=8, head_dim=128, vocab=128256)
+    units = build_layout(d, 8)
+    assert total_params(units) == 8_030_261_248
+    assert units[1].numel == 218_112_000
+    assert units[0].numel + units[-1].numel == 1_050_677_248
+    for u in units:
+        assert u.padded % (8 * 8) == 0 and u.padded - u.numel < 64
+        a, b = u.shard_range(3, 8)
+        assert (b - a) * 8 == u.padded and a % 8 == 0
+    t = build_layout(LlamaDims(hidden=256, ffn=512, layers=2, heads=4, kv_heads=2, head_dim=64, vocab=1024), 1)
+    assert total_params(t) == 1_705_216
+
+
+def test_cu_seqlens_from_position_ids():
+    pos = np.array([[0, 1, 2, 0, 1, 0], [0, 1, 2, 3, 4, 5]])
+    cu, mx = cu_seqlens_from_position_ids(pos)
+    assert cu.tolist() == [0, 3, 5, 6, 12] and mx == 6
+
+
+@pytest.mark.parametrize("name,prec,tol", [("tiny_bf16", "bf16", 1e-3), ("hd128_fp32", "bf16", 4e-3)])
+def test_engine_tracks_reference_fixture(name, prec, tol):
+    """bf16 engine (CPU stand-in kernels) vs the reference run: loss / grad_norm per step, step-0 grads, weights."""
+    z, meta = load(name)
+    cfg = model_cfg(meta)
+    oc = meta["optimizer"]
+    eng = ShardedLlamaEngine(cfg, "cpu", max_tokens=meta["config"]["lbs"] * meta["config"]["seq"], lr=oc["lr"], betas=tuple(oc["betas"]),
+                             eps=oc["eps"], weight_decay=oc["weight_decay"], adam_mode=1, ops=cpu_kernels)
+    eng.load_state_dict(init_params(meta))
+    for s in range(min(3, len(meta["loss"]))):
+        mbs = [_mb(b) for b in batches(z, meta, s)]
+        if s == 0:
+            n = sum(int((m["labels"] != -100).sum()) for m in mbs)
+            eng.loss_dev.zero_()
+            for i, m in enumerate(mbs):
+                eng.forward_backward(m["input_ids"], m["labels"], None, n, first_micro=i == 0, last_micro=i == len(mbs) - 1)
+            for k, g in eng.named_grads().items():
+                check_rel_l2(z, "grad0", k, g.float().numpy(), tol=2e-2)
+            loss = float(eng.loss_dev[0]); gn = float(eng.optimizer_step(meta["max_grad_norm"]).sqrt())
+        else:
+            l, g = eng.train_step(mbs, meta["max_grad_norm"])
+            loss, gn = float(l), float(g)
+        assert abs(loss - meta["loss"][s]) < tol, (s, loss, meta["loss"][s])
+        assert abs(gn - meta["grad_norm"][s]) < 2e-2 * meta["grad_norm"][s], (s, gn, meta["grad_norm"][s])
+        if s in (0, 2) and name == "tiny_bf16":
+            for k, p in eng.state_dict().items():
+                check_summary(z, f"after{s}", k, p.float().numpy(), rtol=2 ** -7, atol=1e-3, outlier_frac=0.01, outlier_atol=2 * oc["lr"] * (s + 1) + 1e-3)
+
+
+def _worker(rank, world, port, name, out_q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    z, meta = load(name)
+    cfg = model_cfg(meta)
+    oc = meta["optimizer"]
+    eng = ShardedLlamaEngine(cfg, "cpu", process_group=dist.group.WORLD, max_tokens=meta["config"]["seq"], lr=oc["lr"], betas=tuple(oc["betas"]),
+                             eps=oc["eps"], weight_decay=oc["weight_decay"], adam_mode=1, ops=cpu_kernels)
+    eng.load_state_dict(init_params(meta))
+    res = []
+    for s in range(2):
+        b = batches(z, meta, s)[0]
+        # each rank takes one sequence of the reference's 2-sequence global batch (data parallel over sequences)
+        mb = {"input_ids": torch.from_numpy(b["input_ids"][rank:rank + 1]), "labels": torch.from_numpy(b["labels"][rank:rank + 1])}
+        l, g = eng.train_step([mb], meta["max_grad_norm"])
+        res.append((float(l), float(g)))
+    # after the step every rank must hold the same, fully gathered parameters
+    flat = torch.cat([p.float().reshape(-1) for p in eng.state_dict().values()])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    same = all(torch.equal(gathered[0], t) for t in gathered)
+    if rank == 0:
+        out_q.put((res, same, {k: v.float().numpy() for k, v in eng.state_dict().items()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_matches_reference_and_single_rank():
+    """world_size 2 over gloo: sharded states, in-place reduce-scatter/all-gather.  The 2-rank run of the reference's global
+    batch must reproduce the reference's loss/grad_norm (fixture: world 1, same global batch) and the single-rank engine."""
+    name = "tiny_bf16"
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res, same, params2 = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert same, "ranks disagree on the gathered parameters"
+    z, meta = load(name)
+    for s, (l, g) in enumerate(res):
+        assert abs(l - meta["loss"][s]) < 1e-3, (s, l, meta["loss"][s])
+        assert abs(g - meta["grad_norm"][s]) < 2e-2 * meta["grad_norm"][s]
+    # single-rank engine, same data as two micro-batches (gradient accumulation)
+    cfg = model_cfg(meta); oc = meta["optimizer"]
+    eng = ShardedLlamaEngine(cfg, "cpu", max_tokens=meta["config"]["seq"], lr=oc["lr"], betas=tuple(oc["betas"]), eps=oc["eps"],
+                             weight_decay=oc["weight_decay"], adam_mode=1, ops=cpu_kernels)
+    eng.load_state_dict(init_params(meta))
+    for s in range(2):
+        b = batches(z, meta, s)[0]
+        mbs = [{"input_ids": torch.from_numpy(b["input_ids"][r:r + 1]), "labels": torch.from_numpy(b["labels"][r:r + 1])} for r in range(2)]
+        l, g = eng.train_step(mbs, meta["max_grad_norm"])
+        assert abs(float(l) - res[s][0]) < 2e-4 and abs(float(g) - res[s][1]) < 5e-3 * res[s][1]
+    worst = 0.0
+    for k, p in eng.state_dict().items():
+        worst = max(worst, float(np.abs(p.float().numpy() - params2[k]).max()))
+    assert worst <= 2 * 2 * oc["lr"] + 1e-3, worst
