@@ -318,17 +318,21 @@ class ShardedLlamaEngine:
             ev = self.streams.event()
             self.streams.record(ev)
             self._in_ev[k] = ev
-        self.ids, self.labels, self.pos = devb[0:T], devb[T:2 * T], devb[2 * T:3 * T]
-        self.cu = devb[3 * T:3 * T + nseq + 1]
-        return T, nseq, max_len
+        return (k, T, nseq, max_len)
 
-    def forward_backward(self, input_ids, labels, position_ids, num_label_tokens, first_micro=True, last_micro=True):
+    def stage(self, input_ids, labels, position_ids=None):
+        """Copy one micro-batch to the device ahead of time; pass the returned handle to forward_backward(staged=...).
+        At most two micro-batches can be resident (two buffer sets)."""
+        return self._stage_inputs(input_ids, labels, position_ids)
+
+    def forward_backward(self, input_ids, labels, position_ids, num_label_tokens, first_micro=True, last_micro=True, staged=None):
         """One micro-batch.  Loss (already divided by the GLOBAL label-token count, train_ft.py:1449-1473) accumulates in
         self.loss_dev; parameter gradients (= or +=) land in the flat gradient buffers; on the last micro-batch each unit's
         gradients are reduce-scattered as soon as its backward is done."""
         ops, d, A, tmp = self.ops, self.dims, self.act, self.tmp
-        T, nseq, max_len = self._stage_inputs(input_ids, labels, position_ids)
-        ids, lab, pos, cu = self.ids, self.labels, self.pos, self.cu
+        k, T, nseq, max_len = staged if staged is not None else self._stage_inputs(input_ids, labels, position_ids)
+        devb = self._in_dev[k]
+        ids, lab, pos, cu = devb[0:T], devb[T:2 * T], devb[2 * T:3 * T], devb[3 * T:3 * T + nseq + 1]
         L, Hq, Hkv, D = d.layers, d.heads, d.kv_heads, d.head_dim
         qc, kc = d.q_cols, d.kv_cols
         rba = self.round_before_add
@@ -430,9 +434,21 @@ class ShardedLlamaEngine:
         self._grads_dirty = False
         return self.norm_sq
 
-    def train_step(self, micro_batches, max_grad_norm: Optional[float] = 1.0, num_label_tokens: Optional[int] = None):
+    def train_step(self, micro_batches, max_grad_norm: Optional[float] = 1.0, num_label_tokens: Optional[int] = None, staged=None):
         """micro_batches: list of dicts with host tensors input_ids / labels [/ position_ids] of shape [b,S].
+        staged: optional list of handles from stage() (inputs already resident on the device; needs num_label_tokens).
         Returns (loss, grad_norm) as 0-d device tensors (no host sync here)."""
+        if staged is not None:
+            assert num_label_tokens is not None
+            self.loss_dev.zero_()
+            for i, hd in enumerate(staged):
+                self.forward_backward(None, None, None, num_label_tokens, first_micro=(i == 0), last_micro=(i == len(staged) - 1), staged=hd)
+            nsq = self.optimizer_step(max_grad_norm)
+            loss = self.loss_dev.clone()
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.pg)
+            return loss[0], nsq.sqrt()[0]
         if num_label_tokens is None:
             n = sum(int((mb["labels"] != IGNORE_INDEX).sum()) for mb in micro_batches)
             if self.world > 1:

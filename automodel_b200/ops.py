@@ -9,6 +9,16 @@ from ._lib import lib, check
 NT, NN, TN = 0, 1, 2
 GEMM_RESIDUAL, GEMM_ROUND_BEFORE_ADD = 1, 2
 
+# number of kernels of THIS library launched so far (bench.py reports the count inside its timed region)
+LAUNCHES = 0
+# optional hook: callable(kind, M, N, K) -> context manager, used by bench.py to time every GEMM launch with CUDA events
+GEMM_TIMER = None
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
 
 def _st():
     return torch.cuda.current_stream().cuda_stream
@@ -47,8 +57,15 @@ def gemm(kind, a, b, out=None, residual=None, round_before_add=True, group_m=0, 
         assert residual.shape == (M, N)
         flags |= GEMM_RESIDUAL | (GEMM_ROUND_BEFORE_ADD if round_before_add else 0)
         ldr = residual.stride(0)
+    if GEMM_TIMER is not None:
+        with GEMM_TIMER(kind, M, N, K):
+            check(lib().b200_gemm_bf16(kind, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0),
+                                       _p(residual), ldr, M, N, K, flags, group_m, max_ctas, _st()), "b200_gemm_bf16")
+        _count(1)
+        return out
     check(lib().b200_gemm_bf16(kind, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0),
                                _p(residual), ldr, M, N, K, flags, group_m, max_ctas, _st()), "b200_gemm_bf16")
+    _count(1)
     return out
 
 
@@ -81,6 +98,7 @@ def rmsnorm_fwd(x, w, eps, out=None, rstd=None):
     if rstd is None:
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
     check(lib().b200_rmsnorm_fwd(x.data_ptr(), w.data_ptr(), out.data_ptr(), rstd.data_ptr(), rows, cols, float(eps), _st()), "b200_rmsnorm_fwd")
+    _count(1)
     return out, rstd
 
 
@@ -97,6 +115,7 @@ def rmsnorm_bwd(dy, x, w, rstd, dres=None, dx=None, dw=None, accumulate_dw=False
         workspace = torch.empty(need, dtype=torch.float32, device=x.device)
     check(lib().b200_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), rstd.data_ptr(), _p(dres), dx.data_ptr(), dw.data_ptr(),
                                  int(accumulate_dw), workspace.data_ptr(), rows, cols, _st()), "b200_rmsnorm_bwd")
+    _count(2)
     return dx, dw
 
 
@@ -105,6 +124,7 @@ def rope_(qk, cos, sin, pos, heads, head_dim, backward=False):
     assert qk.dtype == torch.bfloat16 and qk.stride(1) == 1 and pos.dtype == torch.int32
     check(lib().b200_rope_inplace(qk.data_ptr(), cos.data_ptr(), sin.data_ptr(), pos.data_ptr(), qk.shape[0], heads, head_dim,
                                   qk.stride(0), int(backward), _st()), "b200_rope_inplace")
+    _count(1)
     return qk
 
 
@@ -114,6 +134,7 @@ def swiglu_fwd(gu, out=None):
     if out is None:
         out = torch.empty(T, F2 // 2, dtype=torch.bfloat16, device=gu.device)
     check(lib().b200_swiglu_fwd(gu.data_ptr(), out.data_ptr(), T, F2 // 2, _st()), "b200_swiglu_fwd")
+    _count(1)
     return out
 
 
@@ -123,6 +144,7 @@ def swiglu_bwd(da, gu, out=None):
     if out is None:
         out = torch.empty_like(gu)
     check(lib().b200_swiglu_bwd(da.data_ptr(), gu.data_ptr(), out.data_ptr(), T, F2 // 2, _st()), "b200_swiglu_bwd")
+    _count(1)
     return out
 
 
@@ -132,6 +154,7 @@ def embed_fwd(ids, W, out=None):
     if out is None:
         out = torch.empty(T, W.shape[1], dtype=torch.bfloat16, device=W.device)
     check(lib().b200_embed_fwd(ids.data_ptr(), W.data_ptr(), out.data_ptr(), T, W.shape[1], _st()), "b200_embed_fwd")
+    _count(1)
     return out
 
 
@@ -141,6 +164,7 @@ def embed_bwd(ids, dh, dW, accumulate=False, workspace=None):
         workspace = torch.empty(2 * T, dtype=torch.int32, device=dh.device)
     check(lib().b200_embed_bwd(ids.data_ptr(), dh.data_ptr(), dW.data_ptr(), workspace.data_ptr(), T, dh.shape[1], int(accumulate), _st()),
           "b200_embed_bwd")
+    _count(2)
     return dW
 
 
@@ -155,6 +179,7 @@ def attn_fwd(q, k, v, cu_seqlens, max_seqlen, Hq, Hkv, D, scale=None, out=None, 
     check(lib().b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), cu_seqlens.data_ptr(),
                               cu_seqlens.numel() - 1, max_seqlen, q.stride(0), k.stride(0), v.stride(0), out.stride(0), Hq, Hkv, D, T,
                               float(scale), _st()), "b200_attn_fwd")
+    _count(1)
     return out, lse
 
 
@@ -168,6 +193,7 @@ def attn_bwd(q, k, v, o, dout, lse, cu_seqlens, max_seqlen, Hq, Hkv, D, dq, dk, 
                               dk.data_ptr(), dv.data_ptr(), workspace.data_ptr(), cu_seqlens.data_ptr(), cu_seqlens.numel() - 1,
                               max_seqlen, q.stride(0), k.stride(0), v.stride(0), o.stride(0), dout.stride(0), dq.stride(0),
                               dk.stride(0), dv.stride(0), Hq, Hkv, D, T, float(scale), _st()), "b200_attn_bwd")
+    _count(3)
     return dq, dk, dv
 
 
@@ -179,6 +205,7 @@ def ce_fwd_bwd_(logits, labels, num_label_tokens, loss_out, accumulate=False, ro
         row_loss = torch.empty(T, dtype=torch.float32, device=logits.device)
     check(lib().b200_ce_fwd_bwd(logits.data_ptr(), labels.data_ptr(), row_loss.data_ptr(), loss_out.data_ptr(), T, V, logits.stride(0),
                                 int(num_label_tokens), int(accumulate), _st()), "b200_ce_fwd_bwd")
+    _count(2)
     return loss_out
 
 
@@ -190,14 +217,17 @@ def sumsq_(g, out, accumulate=False):
     if ws is None:
         ws = _ss_ws[g.device] = torch.empty(lib().b200_sumsq_workspace_floats(), dtype=torch.float32, device=g.device)
     check(lib().b200_sumsq_bf16(g.data_ptr(), g.numel(), out.data_ptr(), ws.data_ptr(), int(accumulate), _st()), "b200_sumsq_bf16")
+    _count(2)
     return out
 
 
 def adamw_step_(p, g, m, v, lr, beta1, beta2, eps, wd, step, max_grad_norm=0.0, grad_norm_sq=None, mode=0, master=None):
     check(lib().b200_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(master), p.numel(), lr, beta1, beta2, eps, wd,
                                 int(step), float(max_grad_norm or 0.0), _p(grad_norm_sq), int(mode), _st()), "b200_adamw_step")
+    _count(1)
 
 
 def add_(dst, src):
     check(lib().b200_add_inplace_bf16(dst.data_ptr(), src.data_ptr(), dst.numel(), _st()), "b200_add_inplace_bf16")
+    _count(1)
     return dst

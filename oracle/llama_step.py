@@ -110,7 +110,7 @@ def attention_fwd(q, k, v, scale, seg, P):
     g = Hq // k.shape[1]
     kk = np.repeat(k, g, axis=1)
     vv = np.repeat(v, g, axis=1)
-    s = np.einsum("bhid,bhjd->bhij", q, kk).astype(P.dt) * P.dt(scale)
+    s = (q @ kk.transpose(0, 1, 3, 2)).astype(P.dt) * P.dt(scale)
     mask = np.tril(np.ones((S, S), dtype=bool))[None, None]
     if seg is not None:
         mask = mask & (seg[:, None, :, None] == seg[:, None, None, :])
@@ -118,7 +118,7 @@ def attention_fwd(q, k, v, scale, seg, P):
     m = s.max(-1, keepdims=True)
     p = np.exp(s - m)
     p = p / p.sum(-1, keepdims=True)
-    o = np.einsum("bhij,bhjd->bhid", p, vv)
+    o = p @ vv
     return P.r(o), p
 
 
@@ -128,11 +128,11 @@ def attention_bwd(do, q, k, v, p, scale, P):
     g = Hq // Hkv
     kk = np.repeat(k, g, axis=1)
     vv = np.repeat(v, g, axis=1)
-    dv = np.einsum("bhij,bhid->bhjd", p, do)
-    dp = np.einsum("bhid,bhjd->bhij", do, vv)
+    dv = p.transpose(0, 1, 3, 2) @ do
+    dp = do @ vv.transpose(0, 1, 3, 2)
     ds = p * (dp - (dp * p).sum(-1, keepdims=True)) * P.dt(scale)
-    dq = np.einsum("bhij,bhjd->bhid", ds, kk)
-    dk = np.einsum("bhij,bhid->bhjd", ds, q)
+    dq = ds @ kk
+    dk = ds.transpose(0, 1, 3, 2) @ q
     dk = dk.reshape(b, Hkv, g, S, d).sum(2)
     dv = dv.reshape(b, Hkv, g, S, d).sum(2)
     return P.r(dq), P.r(dk), P.r(dv)
@@ -329,7 +329,46 @@ class AdamW:
         self.t = 0
         self.m, self.v = {}, {}
 
-    def step(self, params, grads):
+    def _step_inplace_threaded(self, params, grads, step_size, bc2_sqrt):
+        """Same update as the loop in step() for fp32/fp64 (no bf16 rounding points), done in place on ~8M-element chunks
+        across a thread pool (numpy releases the GIL), so the timed CPU baseline uses all host cores like torch's CPU ops do."""
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        f = self.P.dt
+        decay, w1, b2, w2, eps = f(1 - self.lr * self.wd), f(1 - self.b1), f(self.b2), f(1 - self.b2), f(self.eps)
+        ss, bs = f(step_size), f(bc2_sqrt)
+        jobs = []
+        for k, p in params.items():
+            if k not in self.m:
+                self.m[k] = np.zeros_like(p, dtype=f)
+                self.v[k] = np.zeros_like(p, dtype=f)
+            if p.dtype != f or not p.flags.c_contiguous:
+                params[k] = p = np.ascontiguousarray(p, dtype=f)
+            g = np.ascontiguousarray(grads[k], dtype=f)
+            pf, gf, mf, vf = p.reshape(-1), g.reshape(-1), self.m[k].reshape(-1), self.v[k].reshape(-1)
+            for a in range(0, pf.size, 1 << 23):
+                jobs.append((pf[a:a + (1 << 23)], gf[a:a + (1 << 23)], mf[a:a + (1 << 23)], vf[a:a + (1 << 23)]))
+
+        def work(j):
+            p, g, m, v = j
+            t = np.empty_like(p)
+            p *= decay
+            np.subtract(g, m, out=t); t *= w1; m += t
+            v *= b2
+            np.multiply(g, g, out=t); t *= w2; v += t
+            np.sqrt(v, out=t); t /= bs; t += eps
+            np.divide(m, t, out=t); t *= ss
+            p -= t
+
+        try:
+            nthr = len(os.sched_getaffinity(0))
+        except Exception:
+            nthr = os.cpu_count() or 1
+        with ThreadPoolExecutor(max_workers=max(1, nthr)) as ex:
+            list(ex.map(work, jobs))
+        return params
+
+    def step(self, params, grads, fast=False):
         P = self.P
         self.t += 1
         f = P.dt
@@ -337,6 +376,8 @@ class AdamW:
         bc2 = 1 - self.b2 ** self.t
         step_size = self.lr / bc1
         bc2_sqrt = math.sqrt(bc2)
+        if fast and not P.bf16:
+            return self._step_inplace_threaded(params, grads, step_size, bc2_sqrt)
         for k, p in params.items():
             g = grads[k].astype(f)
             if k not in self.m:
@@ -358,7 +399,7 @@ class AdamW:
         return params
 
 
-def train_step(params, opt, cfg, micro_batches, prec="fp32", max_grad_norm=1.0):
+def train_step(params, opt, cfg, micro_batches, prec="fp32", max_grad_norm=1.0, timing=False):
     """One optimizer step over a list of micro-batches (recipes/llm/train_ft.py:1482-1635), world size 1.
     micro_batches: list of dicts with input_ids, labels (and optional position_ids).  Returns (loss, grad_norm, grads_pre_clip)."""
     n_lab = int(sum((mb["labels"] != IGNORE_INDEX).sum() for mb in micro_batches))
@@ -368,9 +409,9 @@ def train_step(params, opt, cfg, micro_batches, prec="fp32", max_grad_norm=1.0):
         l, grads = forward_backward(params, cfg, mb["input_ids"], mb["labels"], n_lab, prec,
                                     position_ids=mb.get("position_ids"), grads=grads)
         loss += l
-    pre = {k: v.copy() for k, v in grads.items()}
+    pre = None if timing else {k: v.copy() for k, v in grads.items()}   # timing=True: CPU-baseline run, skip the debug copy
     gn = grad_norm_and_clip(grads, max_grad_norm, prec)
-    opt.step(params, grads)
+    opt.step(params, grads, fast=timing)
     return loss, gn, pre
 
 
