@@ -14,6 +14,7 @@ SIGNATURES = {
     "b200_last_error": (C.c_char_p, []),
     "b200_abi_version": (_i, []),
     "b200_device_check": (_i, []),
+    "b200_set_option": (_i, [C.c_char_p, _i]),
     "b200_gemm_bf16": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b200_gemm_bf16_cublaslt": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "b200_rmsnorm_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),

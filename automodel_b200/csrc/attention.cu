@@ -449,6 +449,22 @@ __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------------------------------------ host
+int attn_delta_launch(const void* o, const void* dout, float* delta, int64_t ldo, int64_t lddo, int Hq, int D, int T, cudaStream_t st) {
+  const int64_t warps = static_cast<int64_t>(T) * Hq;
+  attn_delta_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(o),
+                                                                                static_cast<const __nv_bfloat16*>(dout), delta, ldo, lddo, Hq, D, T);
+  B200_CHECK_LAUNCH("attn_delta");
+  return 0;
+}
+int attn_dq_convert_launch(const float* acc, void* dq, int64_t T, int cols, int64_t lddq, float scale, cudaStream_t st) {
+  const int64_t total = T * (cols / 4);
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  attn_dq_convert_kernel<<<blocks, 256, 0, st>>>(acc, static_cast<__nv_bfloat16*>(dq), T, cols, cols, lddq, scale);
+  B200_CHECK_LAUNCH("attn_dq_convert");
+  return 0;
+}
+
 template <int D>
 static int attn_fwd_launch(const void* q, const void* k, const void* v, void* o, float* lse, const int* cu, int nseq, int max_len,
                            int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int Hq, int Hkv, int T, float scale, cudaStream_t st) {

@@ -3,6 +3,7 @@
 #include <cublasLt.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
 #include <mutex>
 
 #include "../../include/b200_train.h"
@@ -40,6 +41,14 @@ int attn_fwd(const void*, const void*, const void*, void*, float*, const int*, i
 size_t attn_bwd_workspace_bytes(int, int, int);
 int attn_bwd(const void*, const void*, const void*, const void*, const void*, const float*, void*, void*, void*, void*, const int*, int,
              int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, int, int, float, cudaStream_t);
+
+int attn_fwd_tc(const void*, const void*, const void*, void*, float*, const int*, int, int, int64_t, int64_t, int64_t, int64_t, int, int,
+                int, int, float, cudaStream_t);
+int attn_bwd_tc(const void*, const void*, const void*, const void*, const void*, const float*, void*, void*, void*, void*, const int*, int,
+                int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, int, int, float, cudaStream_t);
+
+// debug option: 1 (default) = tcgen05/TMEM attention, 0 = the mma.sync v1 kernels (kept for bisecting only)
+static int g_attn_impl = 1;
 
 // ---------------------------------------------------------------- cuBLASLt comparator (bench / tests only)
 int gemm_bf16_cublaslt(int kind, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K, void* ws,
@@ -102,6 +111,10 @@ extern "C" {
 
 const char* b200_last_error(void) { return g_err; }
 int b200_abi_version(void) { return 1; }
+int b200_set_option(const char* name, int value) {
+  if (name && !strcmp(name, "attn_impl")) { g_attn_impl = value; return 0; }
+  return set_error(B200_ERR_ARG, "unknown option %s", name ? name : "(null)");
+}
 
 int b200_device_check(void) {
   int dev = 0;
@@ -147,6 +160,8 @@ int b200_embed_bwd(const int* ids, const void* dh, void* dW, int* workspace, int
 int b200_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const int* cu_seqlens, int nseq, int max_seqlen,
                   int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int Hq, int Hkv, int head_dim, int total_tokens, float scale,
                   b200_stream_t stream) {
+  if (g_attn_impl == 1)
+    return attn_fwd_tc(q, k, v, o, lse, cu_seqlens, nseq, max_seqlen, ldq, ldk, ldv, ldo, Hq, Hkv, head_dim, total_tokens, scale, S(stream));
   return attn_fwd(q, k, v, o, lse, cu_seqlens, nseq, max_seqlen, ldq, ldk, ldv, ldo, Hq, Hkv, head_dim, total_tokens, scale, S(stream));
 }
 size_t b200_attn_bwd_workspace_bytes(int total_tokens, int Hq, int head_dim) { return attn_bwd_workspace_bytes(total_tokens, Hq, head_dim); }
@@ -154,6 +169,9 @@ int b200_attn_bwd(const void* q, const void* k, const void* v, const void* o, co
                   void* dv, void* workspace, const int* cu_seqlens, int nseq, int max_seqlen, int64_t ldq, int64_t ldk, int64_t ldv,
                   int64_t ldo, int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv, int Hq, int Hkv, int head_dim, int total_tokens,
                   float scale, b200_stream_t stream) {
+  if (g_attn_impl == 1)
+    return attn_bwd_tc(q, k, v, o, dout, lse, dq, dk, dv, workspace, cu_seqlens, nseq, max_seqlen, ldq, ldk, ldv, ldo, lddo, lddq, lddk,
+                       lddv, Hq, Hkv, head_dim, total_tokens, scale, S(stream));
   return attn_bwd(q, k, v, o, dout, lse, dq, dk, dv, workspace, cu_seqlens, nseq, max_seqlen, ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv,
                   Hq, Hkv, head_dim, total_tokens, scale, S(stream));
 }

@@ -32,6 +32,11 @@ def _chk2d(t, name):
     assert t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1, f"{name}: need CUDA bf16 [rows, cols] with unit inner stride"
 
 
+def set_option(name, value):
+    """Debug switches of the library ("attn_impl": 1 = tcgen05 attention (default), 0 = mma.sync v1)."""
+    check(lib().b200_set_option(name.encode(), int(value)), "b200_set_option")
+
+
 def device_check():
     check(lib().b200_device_check(), "b200_device_check")
 

@@ -32,6 +32,8 @@ const char* b200_last_error(void);
 int b200_abi_version(void);
 /* 0 when the current device is sm_100 (B200); B200_ERR_UNSUPPORTED otherwise. */
 int b200_device_check(void);
+/* debug options; "attn_impl": 1 = tcgen05/TMEM attention (default), 0 = mma.sync v1 kernels (bisecting only). */
+int b200_set_option(const char* name, int value);
 
 /* ---- dense contractions: nn.Linear fwd/dgrad/wgrad (components/models/llama/model.py:113-115,151,170,511)
  * kind 0 (NT): C[M,N] = A[M,K] * B[N,K]^T      forward   y = x W^T

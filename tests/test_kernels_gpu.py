@@ -227,9 +227,17 @@ def _attn_ref(q, k, v, cu, Hq, Hkv, D, dout=None):
     return o.detach(), lse.detach(), qf.grad.reshape(T, -1), kf.grad.reshape(T, -1), vf.grad.reshape(T, -1)
 
 
+@pytest.fixture
+def attn_impl(request):
+    ops.set_option("attn_impl", request.param)
+    yield request.param
+    ops.set_option("attn_impl", 1)
+
+
+@pytest.mark.parametrize("attn_impl", [1, 0], indirect=True, ids=["tcgen05", "mma_v1"])
 @pytest.mark.parametrize("D,Hq,Hkv", [(64, 4, 2), (128, 4, 1), (128, 2, 2)])
-@pytest.mark.parametrize("lens", [[512], [64], [1], [200, 57, 255], [130, 1, 64, 63, 65]])
-def test_attention_fwd_bwd(D, Hq, Hkv, lens):
+@pytest.mark.parametrize("lens", [[512], [64], [1], [200, 57, 255], [130, 1, 64, 63, 65], [1024, 129, 127, 128, 300]])
+def test_attention_fwd_bwd(D, Hq, Hkv, lens, attn_impl):
     T = sum(lens)
     cu_list = [0] + list(np.cumsum(lens))
     cu = torch.tensor(cu_list, dtype=torch.int32, device=DEV)
