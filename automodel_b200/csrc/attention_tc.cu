@@ -341,7 +341,7 @@ struct AttnBwdSmem {
 };
 
 template <int D>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(576, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                    const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
@@ -389,9 +389,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(do_full, 1);
     mbar_init(do_empty, 1);
     mbar_init(sdp_full, 1);
-    mbar_init(pt_ready, 4);
+    mbar_init(pt_ready, 16);
     mbar_init(dq_full, 1);
-    mbar_init(dq_free, 4);
+    mbar_init(dq_free, D / 8);   // (D/32 column chunks) x 4 lane quarters
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -481,33 +481,38 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else {
-    // ===================================================== compute warps: thread r <-> kv row n0+r (S^T, dP^T, dK, dV) and q row m0+r (dQ)
-    const int quad = warp & 3;
+    // ===================================================== 16 compute warps.  Warp (quad, chunk): TMEM lanes [32*quad, +32) x 32 columns
+    // [32*chunk, +32).  Thread <-> kv row n0+r (S^T, dP^T, dK, dV) and q row m0+r (dQ).  Four warps per scheduler hide the
+    // TMEM / MUFU / shared-memory latencies that a single warp per scheduler exposes.
+    const int cw = warp - 2;         // 0..15
+    const int quad = warp & 3;       // TMEM lane quarter this warp may access (warp id % 4)
+    const int chunk = cw >> 2;       // 0..3
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const int kv = n0 + r;
-    const int ct = threadIdx.x - 64;  // 0..127
+    const int ct = threadIdx.x - 64;  // 0..511; the first 128 stage the per-q statistics
     constexpr float LOG2E = 1.4426950408889634f;
+    constexpr int OUT_CHUNKS = D / 32;  // column chunks of the dQ / dK / dV tiles
     uint8_t* pt_row = smem + L::PT_OFF + r * 128;
     uint8_t* dst_row = smem + L::DST_OFF + r * 128;
     for (int p = 0; p < n_pairs; ++p) {
       const int h = hk * G + p / pairs_per_head;
       const int mt = nt + p % pairs_per_head;
       const int m0 = mt * 128;
-      // per-q statistics of this pair (parity double-buffer + one named barrier among the 128 compute threads)
+      // per-q statistics of this pair (parity double-buffer + one named barrier among the compute threads)
       float* lse2 = s_lse + (p & 1) * 128;
       float* dlt = s_delta + (p & 1) * 128;
-      {
+      if (ct < 128) {
         const int qi = m0 + ct;
         lse2[ct] = qi < len ? lse[static_cast<int64_t>(h) * T + s0 + qi] * LOG2E : 0.f;
         dlt[ct] = qi < len ? delta[static_cast<int64_t>(h) * T + s0 + qi] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       const bool need_mask = (mt == nt) || (m0 + 128 > len) || (n0 + 128 > len);
       mbar_wait(sdp_full, p & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {  // 32 q columns at a time
+      {
+        const int c = chunk;  // 32 q columns
         uint32_t sv[32], dv_[32];
         tmem_ld_32x32b_x32(tST + lane_addr + c * 32, sv);
         tmem_ld_32x32b_x32(tDP + lane_addr + c * 32, dv_);
@@ -540,60 +545,56 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(pt_ready);
-      // dQ tile of this pair: lane r = q row m0 + r
+      // dQ tile of this pair: lane r = q row m0 + r; every warp waits (the next pair overwrites P^T / dS^T), OUT_CHUNKS*4 warps read
       mbar_wait(dq_full, p & 1);
-      tc_fence_after();
-      const int qi = m0 + r;
-      float* dst = dq_acc + static_cast<int64_t>(s0 + qi) * lddq + h * D;
-#pragma unroll 1
-      for (int c = 0; c < D / 32; ++c) {
+      if (chunk < OUT_CHUNKS) {
+        tc_fence_after();
+        const int qi = m0 + r;
+        float* dst = dq_acc + static_cast<int64_t>(s0 + qi) * lddq + h * D + chunk * 32;
         uint32_t qv[32];
-        tmem_ld_32x32b_x32(tDP + lane_addr + c * 32, qv);
+        tmem_ld_32x32b_x32(tDP + lane_addr + chunk * 32, qv);
         tmem_ld_wait();
         if (qi < len) {
 #pragma unroll
           for (int q4 = 0; q4 < 8; ++q4)
-            atomicAdd(reinterpret_cast<float4*>(dst + c * 32 + q4 * 4),
+            atomicAdd(reinterpret_cast<float4*>(dst + q4 * 4),
                       make_float4(__uint_as_float(qv[q4 * 4]), __uint_as_float(qv[q4 * 4 + 1]), __uint_as_float(qv[q4 * 4 + 2]),
                                   __uint_as_float(qv[q4 * 4 + 3])));
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_free);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(dq_free);
     }
     // final dK (scaled) / dV rows; dq_full of the last pair covers every MMA of the CTA
     mbar_wait(dq_full, (n_pairs - 1) & 1);
-    tc_fence_after();
-    {
+    if (chunk < OUT_CHUNKS) {
+      tc_fence_after();
       const bool valid = kv < len;  // tcgen05.ld is warp-collective: every lane loads, only valid rows store
-      __nv_bfloat16* dkr = dk + static_cast<int64_t>(s0 + kv) * lddk + hk * D;
-      __nv_bfloat16* dvr = dv + static_cast<int64_t>(s0 + kv) * lddv + hk * D;
-#pragma unroll 1
-      for (int c = 0; c < D / 32; ++c) {
-        uint32_t a[32], b[32];
-        tmem_ld_32x32b_x32(tDK + lane_addr + c * 32, a);
-        tmem_ld_32x32b_x32(tDV + lane_addr + c * 32, b);
-        tmem_ld_wait();
-        if (valid) {
+      __nv_bfloat16* dkr = dk + static_cast<int64_t>(s0 + kv) * lddk + hk * D + chunk * 32;
+      __nv_bfloat16* dvr = dv + static_cast<int64_t>(s0 + kv) * lddv + hk * D + chunk * 32;
+      uint32_t a[32], b[32];
+      tmem_ld_32x32b_x32(tDK + lane_addr + chunk * 32, a);
+      tmem_ld_32x32b_x32(tDV + lane_addr + chunk * 32, b);
+      tmem_ld_wait();
+      if (valid) {
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint4 x, y;
-            x.x = pack_bf16x2(__uint_as_float(a[q4 * 8 + 0]) * scale, __uint_as_float(a[q4 * 8 + 1]) * scale);
-            x.y = pack_bf16x2(__uint_as_float(a[q4 * 8 + 2]) * scale, __uint_as_float(a[q4 * 8 + 3]) * scale);
-            x.z = pack_bf16x2(__uint_as_float(a[q4 * 8 + 4]) * scale, __uint_as_float(a[q4 * 8 + 5]) * scale);
-            x.w = pack_bf16x2(__uint_as_float(a[q4 * 8 + 6]) * scale, __uint_as_float(a[q4 * 8 + 7]) * scale);
-            y.x = pack_bf16x2(__uint_as_float(b[q4 * 8 + 0]), __uint_as_float(b[q4 * 8 + 1]));
-            y.y = pack_bf16x2(__uint_as_float(b[q4 * 8 + 2]), __uint_as_float(b[q4 * 8 + 3]));
-            y.z = pack_bf16x2(__uint_as_float(b[q4 * 8 + 4]), __uint_as_float(b[q4 * 8 + 5]));
-            y.w = pack_bf16x2(__uint_as_float(b[q4 * 8 + 6]), __uint_as_float(b[q4 * 8 + 7]));
-            *reinterpret_cast<uint4*>(dkr + c * 32 + q4 * 8) = x;
-            *reinterpret_cast<uint4*>(dvr + c * 32 + q4 * 8) = y;
-          }
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 x, y;
+          x.x = pack_bf16x2(__uint_as_float(a[q4 * 8 + 0]) * scale, __uint_as_float(a[q4 * 8 + 1]) * scale);
+          x.y = pack_bf16x2(__uint_as_float(a[q4 * 8 + 2]) * scale, __uint_as_float(a[q4 * 8 + 3]) * scale);
+          x.z = pack_bf16x2(__uint_as_float(a[q4 * 8 + 4]) * scale, __uint_as_float(a[q4 * 8 + 5]) * scale);
+          x.w = pack_bf16x2(__uint_as_float(a[q4 * 8 + 6]) * scale, __uint_as_float(a[q4 * 8 + 7]) * scale);
+          y.x = pack_bf16x2(__uint_as_float(b[q4 * 8 + 0]), __uint_as_float(b[q4 * 8 + 1]));
+          y.y = pack_bf16x2(__uint_as_float(b[q4 * 8 + 2]), __uint_as_float(b[q4 * 8 + 3]));
+          y.z = pack_bf16x2(__uint_as_float(b[q4 * 8 + 4]), __uint_as_float(b[q4 * 8 + 5]));
+          y.w = pack_bf16x2(__uint_as_float(b[q4 * 8 + 6]), __uint_as_float(b[q4 * 8 + 7]));
+          *reinterpret_cast<uint4*>(dkr + q4 * 8) = x;
+          *reinterpret_cast<uint4*>(dvr + q4 * 8) = y;
         }
       }
+      tc_fence_before();
     }
-    tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
@@ -630,7 +631,7 @@ static int attn_bwd_tc_launch(const void* q, const void* k, const void* v, const
   if ((rc = make_tmap_2d_bf16(&tv, v, T, static_cast<uint64_t>(Hkv) * D, ldv, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tdo, dout, T, static_cast<uint64_t>(Hq) * D, lddo, 64, 128))) return rc;
   dim3 grid((max_len + 127) / 128, Hkv, nseq);
-  kern<<<grid, 192, L::DYN, st>>>(tq, tk, tv, tdo, lse, delta, dq_acc, static_cast<__nv_bfloat16*>(dk), static_cast<__nv_bfloat16*>(dv), cu,
+  kern<<<grid, 576, L::DYN, st>>>(tq, tk, tv, tdo, lse, delta, dq_acc, static_cast<__nv_bfloat16*>(dk), static_cast<__nv_bfloat16*>(dv), cu,
                                   static_cast<int64_t>(Hq) * D, lddk, lddv, Hq, Hkv, T, scale, scale * 1.4426950408889634f);
   B200_CHECK_LAUNCH("attn_bwd_tc");
   return attn_dq_convert_launch(dq_acc, dq, T, Hq * D, lddq, scale, st);

@@ -634,6 +634,22 @@ int sumsq_bf16(const void* g, int64_t n, float* out, float* ws, int accumulate, 
 // mode 0: fp32 math, one rounding per stored tensor (and fp32 master weights when given).
 // mode 1: torch's op sequence on bf16 tensors (mul_, lerp_, mul_, addcmul_, sqrt, div_, add_, addcdiv_), every op
 //         materialised in bf16, which is what torch.optim.AdamW does to bf16 params/states.
+__device__ __forceinline__ void round2(float& x, float& y) {  // (x, y) -> bf16 -> fp32, 3 instructions for two values
+  const __nv_bfloat162 t = __floats2bfloat162_rn(x, y);
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(&t);
+  x = __uint_as_float(u << 16);
+  y = __uint_as_float(u & 0xffff0000u);
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 struct AdamWArgs {  // scalars are formed in double on the host (as torch does in Python) and rounded to fp32 once
   float decay, step_size, beta1, w1, beta2, w2, eps, bc2_sqrt, max_norm;
 };
@@ -657,21 +673,37 @@ __global__ void __launch_bounds__(256) adamw_kernel(__nv_bfloat16* __restrict__ 
       const float4 a0 = reinterpret_cast<const float4*>(master)[2 * i], a1 = reinterpret_cast<const float4*>(master)[2 * i + 1];
       pf[0] = a0.x; pf[1] = a0.y; pf[2] = a0.z; pf[3] = a0.w; pf[4] = a1.x; pf[5] = a1.y; pf[6] = a1.z; pf[7] = a1.w;
     }
+    if (MODE == 1) {
+      // torch's op sequence, two elements at a time: every materialised bf16 tensor is one packed cvt.rn.bf16x2 + two bit ops.
+      // sqrt / reciprocal use the MUFU approximations (<= 2 ulp fp32, i.e. 2^-14 of a bf16 ulp): the kernel stays HBM-bound.
+      const float inv_bc2 = 1.f / a.bc2_sqrt;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      if (MODE == 1) {
-        const float gg = bf16_round(gf[e] * coef);
-        float pp = bf16_round(pf[e] * decay);
-        const float w1 = a.w1;
-        float mm = w1 < 0.5f ? bf16_round(mf[e] + w1 * (gg - mf[e])) : bf16_round(gg - (gg - mf[e]) * (1.f - w1));
-        float vv = bf16_round(vf[e] * a.beta2);
-        vv = bf16_round(vv + a.w2 * gg * gg);
-        float den = bf16_round(sqrtf(vv));
-        den = bf16_round(den / a.bc2_sqrt);
-        den = bf16_round(den + a.eps);
-        pp = bf16_round(pp + (-step_size) * (mm / den));
-        pf[e] = pp; mf[e] = mm; vf[e] = vv;
-      } else {
+      for (int e = 0; e < 8; e += 2) {
+        float g0 = gf[e] * coef, g1 = gf[e + 1] * coef;
+        round2(g0, g1);
+        float p0 = pf[e] * decay, p1 = pf[e + 1] * decay;
+        round2(p0, p1);
+        float m0 = mf[e] + a.w1 * (g0 - mf[e]), m1 = mf[e + 1] + a.w1 * (g1 - mf[e + 1]);  // lerp_, weight < 0.5
+        round2(m0, m1);
+        float v0 = vf[e] * a.beta2, v1 = vf[e + 1] * a.beta2;
+        round2(v0, v1);
+        v0 = v0 + (a.w2 * g0) * g0;
+        v1 = v1 + (a.w2 * g1) * g1;
+        round2(v0, v1);
+        float d0 = sqrt_approx(v0), d1 = sqrt_approx(v1);
+        round2(d0, d1);
+        d0 *= inv_bc2; d1 *= inv_bc2;
+        round2(d0, d1);
+        d0 += a.eps; d1 += a.eps;
+        round2(d0, d1);
+        p0 = p0 - step_size * (m0 * rcp_approx(d0));
+        p1 = p1 - step_size * (m1 * rcp_approx(d1));
+        round2(p0, p1);
+        pf[e] = p0; pf[e + 1] = p1; mf[e] = m0; mf[e + 1] = m1; vf[e] = v0; vf[e + 1] = v1;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
         const float gg = gf[e] * coef;
         const float mm = a.beta1 * mf[e] + a.w1 * gg;
         const float vv = a.beta2 * vf[e] + a.w2 * gg * gg;
