@@ -278,6 +278,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // ------------------------------------------------------------------------------------------------ host
 int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
                       uint32_t box_rows);
+int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                     uint32_t box_rows);
 
 template <int D>
 static int attn_fwd_tc_launch(const void* q, const void* k, const void* v, void* o, float* lse, const int* cu, int nseq, int max_len,
@@ -344,9 +346,9 @@ template <int D>
 __global__ void __launch_bounds__(576, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
-                   const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
+                   const __grid_constant__ CUtensorMap tmDQ, const float* __restrict__ lse, const float* __restrict__ delta,
                    __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, const int* __restrict__ cu_seqlens,
-                   int64_t lddq, int64_t lddk, int64_t lddv, int Hq, int Hkv, int T, float scale, float scale_log2) {
+                   int64_t lddk, int64_t lddv, int Hq, int Hkv, int T, float scale, float scale_log2) {
   using L = AttnBwdSmem<D>;
   constexpr int ATOMS = D / 64;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -381,6 +383,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDQ);
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
@@ -507,6 +510,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         lse2[ct] = qi < len ? lse[static_cast<int64_t>(h) * T + s0 + qi] * LOG2E : 0.f;
         dlt[ct] = qi < len ? delta[static_cast<int64_t>(h) * T + s0 + qi] : 0.f;
       }
+      if (chunk < OUT_CHUNKS && quad == 0 && lane == 0) tma_store_wait_read<0>();  // previous pair's dQ staging has been read out
       asm volatile("bar.sync 1, 512;" ::: "memory");
       const bool need_mask = (mt == nt) || (m0 + 128 > len) || (n0 + 128 > len);
       mbar_wait(sdp_full, p & 1);
@@ -545,27 +549,32 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(pt_ready);
-      // dQ tile of this pair: lane r = q row m0 + r; every warp waits (the next pair overwrites P^T / dS^T), OUT_CHUNKS*4 warps read
+      // dQ tile of this pair (lane r = q row m0 + r).  Every warp waits (the next pair overwrites P^T / dS^T); the OUT_CHUNKS*4
+      // warps that own a column chunk copy it TMEM -> registers -> swizzled fp32 staging (the now idle P^T/dS^T buffers) and
+      // ONE thread per chunk issues a TMA reduce-add of the [128 x 32] fp32 box into the dq accumulator: 4 bulk L2 reductions per
+      // pair instead of 4096 vector atomics.  Rows past the sequence end carry exact zeros (their dS is masked).
       mbar_wait(dq_full, p & 1);
       if (chunk < OUT_CHUNKS) {
         tc_fence_after();
-        const int qi = m0 + r;
-        float* dst = dq_acc + static_cast<int64_t>(s0 + qi) * lddq + h * D + chunk * 32;
         uint32_t qv[32];
         tmem_ld_32x32b_x32(tDP + lane_addr + chunk * 32, qv);
         tmem_ld_wait();
-        if (qi < len) {
-#pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4)
-            atomicAdd(reinterpret_cast<float4*>(dst + q4 * 4),
-                      make_float4(__uint_as_float(qv[q4 * 4]), __uint_as_float(qv[q4 * 4 + 1]), __uint_as_float(qv[q4 * 4 + 2]),
-                                  __uint_as_float(qv[q4 * 4 + 3])));
-        }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(dq_free);
+        if (lane == 0) mbar_arrive(dq_free);  // the dP^T / dQ columns may be overwritten by dP^T_{p+1}
+        uint8_t* stage = smem + L::PT_OFF + chunk * 16384 + r * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4)
+          *reinterpret_cast<uint4*>(stage + ((q4 ^ (r & 7)) << 4)) = make_uint4(qv[q4 * 4], qv[q4 * 4 + 1], qv[q4 * 4 + 2], qv[q4 * 4 + 3]);
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + chunk) : "memory");  // the four lane-quarter warps of this chunk
+        if (quad == 0 && lane == 0) {
+          tma_reduce_add_2d(&tmDQ, smem + L::PT_OFF + chunk * 16384, h * D + chunk * 32, s0 + m0);
+          tma_store_commit();
+        }
       }
     }
+    if (chunk < OUT_CHUNKS && quad == 0 && lane == 0) tma_store_wait<0>();
     // final dK (scaled) / dV rows; dq_full of the last pair covers every MMA of the CTA
     mbar_wait(dq_full, (n_pairs - 1) & 1);
     if (chunk < OUT_CHUNKS) {
@@ -625,14 +634,15 @@ static int attn_bwd_tc_launch(const void* q, const void* k, const void* v, const
   if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "attn_bwd memset: %s", cudaGetErrorString(e));
   int rc;
   if ((rc = attn_delta_launch(o, dout, delta, ldo, lddo, Hq, D, T, st))) return rc;
-  CUtensorMap tq, tk, tv, tdo;
+  CUtensorMap tq, tk, tv, tdo, tdq;
+  if ((rc = make_tmap_2d_f32(&tdq, dq_acc, T, static_cast<uint64_t>(Hq) * D, static_cast<uint64_t>(Hq) * D, 32, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tq, q, T, static_cast<uint64_t>(Hq) * D, ldq, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tk, k, T, static_cast<uint64_t>(Hkv) * D, ldk, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tv, v, T, static_cast<uint64_t>(Hkv) * D, ldv, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tdo, dout, T, static_cast<uint64_t>(Hq) * D, lddo, 64, 128))) return rc;
   dim3 grid((max_len + 127) / 128, Hkv, nseq);
-  kern<<<grid, 576, L::DYN, st>>>(tq, tk, tv, tdo, lse, delta, dq_acc, static_cast<__nv_bfloat16*>(dk), static_cast<__nv_bfloat16*>(dv), cu,
-                                  static_cast<int64_t>(Hq) * D, lddk, lddv, Hq, Hkv, T, scale, scale * 1.4426950408889634f);
+  kern<<<grid, 576, L::DYN, st>>>(tq, tk, tv, tdo, tdq, lse, delta, static_cast<__nv_bfloat16*>(dk), static_cast<__nv_bfloat16*>(dv), cu,
+                                  lddk, lddv, Hq, Hkv, T, scale, scale * 1.4426950408889634f);
   B200_CHECK_LAUNCH("attn_bwd_tc");
   return attn_dq_convert_launch(dq_acc, dq, T, Hq * D, lddq, scale, st);
 }

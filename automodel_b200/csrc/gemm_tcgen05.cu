@@ -297,18 +297,28 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// 2D bf16 row-major tensor [rows, cols] with leading dimension ld (elements); box = (box_cols, box_rows), 128B swizzle.
+// 2D row-major tensor [rows, cols] with leading dimension ld (elements); box = (box_cols, box_rows), 128B swizzle.
+static int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                        uint32_t box_rows, CUtensorMapDataType dt, int esize);
 int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
                       uint32_t box_rows) {
+  return make_tmap_2d(out, ptr, rows, cols, ld, box_cols, box_rows, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+}
+int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                     uint32_t box_rows) {
+  return make_tmap_2d(out, ptr, rows, cols, ld, box_cols, box_rows, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4);
+}
+static int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                        uint32_t box_rows, CUtensorMapDataType dt, int esize) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return set_error(B200_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not found");
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15))
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * esize) & 15))
     return set_error(B200_ERR_ARG, "TMA operand must be 16B aligned with a 16B-multiple row pitch");
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstr[1] = {ld * 2};
+  cuuint64_t gstr[1] = {ld * esize};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+  CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(B200_ERR_DRIVER, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
