@@ -13,6 +13,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <math.h>
+#include <stdio.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -326,6 +327,15 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse
 // with 16-byte vector atomics.
 namespace b200 {
 
+#ifdef B200_ATTN_PROFILE
+__device__ unsigned long long g_attn_prof[32];
+#define PROF_DECL unsigned long long pt0 = clock64(), pt1
+#define PROF(slot) do { pt1 = clock64(); if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) atomicAdd(&g_attn_prof[slot], pt1 - pt0); pt0 = pt1; } while (0)
+#else
+#define PROF_DECL
+#define PROF(slot)
+#endif
+
 template <int D>
 struct AttnBwdSmem {
   static constexpr int TILE = 128 * D * 2;
@@ -338,12 +348,12 @@ struct AttnBwdSmem {
   static constexpr int DST_OFF = PT_OFF + PT_BYTES;
   static constexpr int LSE_OFF = DST_OFF + PT_BYTES;          // float [2][128] lse*log2e, then [2][128] delta
   static constexpr int BAR_OFF = LSE_OFF + 4 * 128 * 4;
-  static constexpr int NUM_BARS = 1 + 2 + 2 + 1 + 1 + 1 + 1 + 1 + 1;  // kv_full, q_full[2], q_empty[2], do_full, do_empty, sdp_full, pt_ready, dq_full, dq_free
+  static constexpr int NUM_BARS = 1 + 2 + 2 + 1 + 1 + 1 + 1 + 1 + 1 + 1;  // kv_full, q_full[2], q_empty[2], do_full, do_empty, sdp_full, pt_ready, dq_full, dq_free, pa_ready
   static constexpr int DYN = BAR_OFF + NUM_BARS * 8 + 16;   // 231,528 B at D=128: no room for manual alignment slack
 };
 
 template <int D>
-__global__ void __launch_bounds__(576, 1)
+__global__ void __maxnreg__(112)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmDQ, const float* __restrict__ lse, const float* __restrict__ delta,
@@ -363,6 +373,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* pt_ready = bars + 8;
   uint64_t* dq_full = bars + 9;
   uint64_t* dq_free = bars + 10;
+  uint64_t* pa_ready = bars + 11;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
   float* s_lse = reinterpret_cast<float*>(smem + L::LSE_OFF);  // [2][128]
   float* s_delta = s_lse + 256;                                 // [2][128]
@@ -393,6 +404,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(do_empty, 1);
     mbar_init(sdp_full, 1);
     mbar_init(pt_ready, 16);
+    mbar_init(pa_ready, 16);
     mbar_init(dq_full, 1);
     mbar_init(dq_free, D / 8);   // (D/32 column chunks) x 4 lane quarters
     fence_mbar_init();
@@ -440,11 +452,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t do_base = smem_u32(smem + L::DO_OFF);
       const uint32_t pt_base = smem_u32(smem + L::PT_OFF), dst_base = smem_u32(smem + L::DST_OFF);
       mbar_wait(kv_full, 0);
+      PROF_DECL;
       for (int p = 0; p < n_pairs; ++p) {
         const int st = p & 1;
         const uint32_t q_base = smem_u32(smem + L::Q_OFF + st * L::TILE);
         // S^T (the compute warps finished loading S^T_{p-1} before pt_ready_{p-1}, which this thread has waited on)
         mbar_wait(&q_full[st], (p >> 1) & 1);
+        PROF(0);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
@@ -452,8 +466,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           umma_bf16(tST, make_smem_desc_sw128(k_base + off, 16, 1024), make_smem_desc_sw128(q_base + off, 16, 1024), idesc_st, kk != 0);
         }
         // dP^T goes where dQ_{p-1} lives: wait until it has been read out
+        PROF(1);
         mbar_wait(do_full, p & 1);
+        PROF(2);
         mbar_wait(dq_free, (p & 1) ^ 1);
+        PROF(3);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
@@ -461,7 +478,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           umma_bf16(tDP, make_smem_desc_sw128(v_base + off, 16, 1024), make_smem_desc_sw128(do_base + off, 16, 1024), idesc_st, kk != 0);
         }
         umma_commit(sdp_full);
-        mbar_wait(pt_ready, p & 1);
+        PROF(4);
+        mbar_wait(pa_ready, p & 1);   // P^T is in smem (dS^T still being computed: dV overlaps it)
         tc_fence_after();
         // dV += P^T dO      A: P^T [kv x q] K-major (2 atoms of 64 q);  B: dO [q x d] MN-major
 #pragma unroll
@@ -469,6 +487,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           umma_bf16(tDV, make_smem_desc_sw128(pt_base + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                     make_smem_desc_sw128(do_base + kk * 2048, 16384, 1024), idesc_dkv, (p | kk) != 0);
         umma_commit(do_empty);
+        mbar_wait(pt_ready, p & 1);
+        PROF(5);
+        tc_fence_after();
         // dK += dS^T Q
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
@@ -481,6 +502,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           umma_bf16(tDP, make_smem_desc_sw128(dst_base + kk * 2048, 16384, 1024), make_smem_desc_sw128(k_base + kk * 2048, 16384, 1024),
                     idesc_dq, kk != 0);
         umma_commit(dq_full);
+        PROF(6);
       }
     }
   } else {
@@ -498,62 +520,114 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     constexpr int OUT_CHUNKS = D / 32;  // column chunks of the dQ / dK / dV tiles
     uint8_t* pt_row = smem + L::PT_OFF + r * 128;
     uint8_t* dst_row = smem + L::DST_OFF + r * 128;
+#ifdef B200_ATTN_PROFILE
+    unsigned long long pt0 = clock64(), pt1;
+#define CPROF(slot) do { if (warp == 2 && lane == 0) { pt1 = clock64(); if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) atomicAdd(&g_attn_prof[slot], pt1 - pt0); pt0 = pt1; } } while (0)
+#else
+#define CPROF(slot)
+#endif
+    // per-q statistics (lse*log2e, delta) of the NEXT pair are fetched one pair ahead into registers of the first 128 threads
+    float nxt_lse = 0.f, nxt_dlt = 0.f;
+    if (ct < 128) {
+      const int qi = nt * 128 + ct;  // pair 0: head hk*G, q tile nt
+      if (qi < len) {
+        nxt_lse = lse[static_cast<int64_t>(hk * G) * T + s0 + qi] * LOG2E;
+        nxt_dlt = delta[static_cast<int64_t>(hk * G) * T + s0 + qi];
+      }
+    }
+    int h = hk * G, mt = nt;
     for (int p = 0; p < n_pairs; ++p) {
-      const int h = hk * G + p / pairs_per_head;
-      const int mt = nt + p % pairs_per_head;
       const int m0 = mt * 128;
-      // per-q statistics of this pair (parity double-buffer + one named barrier among the compute threads)
+      int h_n = h, mt_n = mt + 1;
+      if (mt_n == mt_end) {
+        mt_n = nt;
+        ++h_n;
+      }
       float* lse2 = s_lse + (p & 1) * 128;
       float* dlt = s_delta + (p & 1) * 128;
       if (ct < 128) {
-        const int qi = m0 + ct;
-        lse2[ct] = qi < len ? lse[static_cast<int64_t>(h) * T + s0 + qi] * LOG2E : 0.f;
-        dlt[ct] = qi < len ? delta[static_cast<int64_t>(h) * T + s0 + qi] : 0.f;
+        lse2[ct] = nxt_lse;
+        dlt[ct] = nxt_dlt;
+        nxt_lse = nxt_dlt = 0.f;
+        const int qi = mt_n * 128 + ct;
+        if (p + 1 < n_pairs && qi < len) {
+          nxt_lse = lse[static_cast<int64_t>(h_n) * T + s0 + qi] * LOG2E;
+          nxt_dlt = delta[static_cast<int64_t>(h_n) * T + s0 + qi];
+        }
       }
       if (chunk < OUT_CHUNKS && quad == 0 && lane == 0) tma_store_wait_read<0>();  // previous pair's dQ staging has been read out
       asm volatile("bar.sync 1, 512;" ::: "memory");
+      CPROF(8);
       const bool need_mask = (mt == nt) || (m0 + 128 > len) || (n0 + 128 > len);
       mbar_wait(sdp_full, p & 1);
+      CPROF(9);
       tc_fence_after();
       {
-        const int c = chunk;  // 32 q columns
+        const int c = chunk;  // this warp's 32 q columns
         uint32_t sv[32], dv_[32];
         tmem_ld_32x32b_x32(tST + lane_addr + c * 32, sv);
         tmem_ld_32x32b_x32(tDP + lane_addr + c * 32, dv_);
         tmem_ld_wait();
-        uint32_t pp[16], dd[16];
+        // ---- phase A: P^T = 2^(S^T * scale*log2e - lse*log2e)  -> smem; the MMA warp starts dV += P^T dO right away
+        const float4* l4 = reinterpret_cast<const float4*>(lse2 + c * 32);
+        float pf[32];
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float pv[2], ds[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int qc = c * 32 + e + u;
-            float x = ex2_approx(__uint_as_float(sv[e + u]) * scale_log2 - lse2[qc]);
-            if (need_mask && ((m0 + qc) < kv || (m0 + qc) >= len || kv >= len)) x = 0.f;
-            pv[u] = x;
-            ds[u] = x * (__uint_as_float(dv_[e + u]) - dlt[qc]);
-          }
-          pp[e >> 1] = pack_bf16x2(pv[0], pv[1]);
-          dd[e >> 1] = pack_bf16x2(ds[0], ds[1]);
+        for (int e4 = 0; e4 < 8; ++e4) {
+          const float4 ls = l4[e4];
+          pf[e4 * 4 + 0] = ex2_approx(__uint_as_float(sv[e4 * 4 + 0]) * scale_log2 - ls.x);
+          pf[e4 * 4 + 1] = ex2_approx(__uint_as_float(sv[e4 * 4 + 1]) * scale_log2 - ls.y);
+          pf[e4 * 4 + 2] = ex2_approx(__uint_as_float(sv[e4 * 4 + 2]) * scale_log2 - ls.z);
+          pf[e4 * 4 + 3] = ex2_approx(__uint_as_float(sv[e4 * 4 + 3]) * scale_log2 - ls.w);
         }
-        // the previous pair's dV/dK/dQ MMAs (readers of these tiles) completed before dq_full_{p-1}, which this thread waited on
+        if (need_mask) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int qc = m0 + c * 32 + e;
+            if (qc < kv || qc >= len || kv >= len) pf[e] = 0.f;
+          }
+        }
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           const int ch = c * 4 + q4;  // 16-byte chunk = 8 q columns; atom = ch / 8
           const uint32_t off = (ch >> 3) * 16384 + (((ch & 7) ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(pt_row + off) = make_uint4(pp[q4 * 4], pp[q4 * 4 + 1], pp[q4 * 4 + 2], pp[q4 * 4 + 3]);
-          *reinterpret_cast<uint4*>(dst_row + off) = make_uint4(dd[q4 * 4], dd[q4 * 4 + 1], dd[q4 * 4 + 2], dd[q4 * 4 + 3]);
+          *reinterpret_cast<uint4*>(pt_row + off) =
+              make_uint4(pack_bf16x2(pf[q4 * 8 + 0], pf[q4 * 8 + 1]), pack_bf16x2(pf[q4 * 8 + 2], pf[q4 * 8 + 3]),
+                         pack_bf16x2(pf[q4 * 8 + 4], pf[q4 * 8 + 5]), pack_bf16x2(pf[q4 * 8 + 6], pf[q4 * 8 + 7]));
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pa_ready);
+        // ---- phase B: dS^T = P^T * (dP^T - delta) -> smem
+        const float4* d4 = reinterpret_cast<const float4*>(dlt + c * 32);
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4) {
+          const float4 dl = d4[e4];
+          pf[e4 * 4 + 0] *= __uint_as_float(dv_[e4 * 4 + 0]) - dl.x;
+          pf[e4 * 4 + 1] *= __uint_as_float(dv_[e4 * 4 + 1]) - dl.y;
+          pf[e4 * 4 + 2] *= __uint_as_float(dv_[e4 * 4 + 2]) - dl.z;
+          pf[e4 * 4 + 3] *= __uint_as_float(dv_[e4 * 4 + 3]) - dl.w;
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int ch = c * 4 + q4;
+          const uint32_t off = (ch >> 3) * 16384 + (((ch & 7) ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst_row + off) =
+              make_uint4(pack_bf16x2(pf[q4 * 8 + 0], pf[q4 * 8 + 1]), pack_bf16x2(pf[q4 * 8 + 2], pf[q4 * 8 + 3]),
+                         pack_bf16x2(pf[q4 * 8 + 4], pf[q4 * 8 + 5]), pack_bf16x2(pf[q4 * 8 + 6], pf[q4 * 8 + 7]));
         }
       }
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(pt_ready);
+      CPROF(10);
       // dQ tile of this pair (lane r = q row m0 + r).  Every warp waits (the next pair overwrites P^T / dS^T); the OUT_CHUNKS*4
       // warps that own a column chunk copy it TMEM -> registers -> swizzled fp32 staging (the now idle P^T/dS^T buffers) and
       // ONE thread per chunk issues a TMA reduce-add of the [128 x 32] fp32 box into the dq accumulator: 4 bulk L2 reductions per
       // pair instead of 4096 vector atomics.  Rows past the sequence end carry exact zeros (their dS is masked).
       mbar_wait(dq_full, p & 1);
+      CPROF(11);
       if (chunk < OUT_CHUNKS) {
         tc_fence_after();
         uint32_t qv[32];
@@ -573,6 +647,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tma_store_commit();
         }
       }
+      CPROF(12);
+      h = h_n;
+      mt = mt_n;
     }
     if (chunk < OUT_CHUNKS && quad == 0 && lane == 0) tma_store_wait<0>();
     // final dK (scaled) / dV rows; dq_full of the last pair covers every MMA of the CTA
@@ -644,6 +721,19 @@ static int attn_bwd_tc_launch(const void* q, const void* k, const void* v, const
   kern<<<grid, 576, L::DYN, st>>>(tq, tk, tv, tdo, tdq, lse, delta, static_cast<__nv_bfloat16*>(dk), static_cast<__nv_bfloat16*>(dv), cu,
                                   lddk, lddv, Hq, Hkv, T, scale, scale * 1.4426950408889634f);
   B200_CHECK_LAUNCH("attn_bwd_tc");
+#ifdef B200_ATTN_PROFILE
+  {
+    cudaStreamSynchronize(st);
+    unsigned long long h[32];
+    cudaMemcpyFromSymbol(h, g_attn_prof, sizeof(h));
+    static const char* names[] = {"mma:wait q_full", "mma:issue S^T", "mma:wait do_full", "mma:wait dq_free", "mma:issue dP^T", "mma:wait pt_ready",
+                                  "mma:issue dV,dK,dQ", "", "cmp:stats+bar", "cmp:wait sdp_full", "cmp:compute+store", "cmp:wait dq_full", "cmp:dq readout"};
+    const int npairs = (Hq / Hkv) * ((max_len + 127) / 128);
+    for (int i = 0; i < 13; ++i) if (names[i][0]) fprintf(stderr, "ATTN_PROF %-22s %8.0f cycles/pair\n", names[i], double(h[i]) / npairs);
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(g_attn_prof, z, sizeof(z));
+  }
+#endif
   return attn_dq_convert_launch(dq_acc, dq, T, Hq * D, lddq, scale, st);
 }
 
