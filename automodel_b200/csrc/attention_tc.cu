@@ -353,7 +353,7 @@ struct AttnBwdSmem {
 };
 
 template <int D>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(576, 1)  // 18 warps: 5 on two of the four schedulers -> at most 16384/(5*32) = 102 registers per thread
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmDQ, const float* __restrict__ lse, const float* __restrict__ delta,
