@@ -348,7 +348,7 @@ struct AttnBwdSmem {
   static constexpr int DST_OFF = PT_OFF + PT_BYTES;
   static constexpr int LSE_OFF = DST_OFF + PT_BYTES;          // float [2][128] lse*log2e, then [2][128] delta
   static constexpr int BAR_OFF = LSE_OFF + 4 * 128 * 4;
-  static constexpr int NUM_BARS = 1 + 2 + 2 + 1 + 1 + 1 + 1 + 1 + 1 + 1;  // kv_full, q_full[2], q_empty[2], do_full, do_empty, sdp_full, pt_ready, dq_full, dq_free, pa_ready
+  static constexpr int NUM_BARS = 1 + 2 + 2 + 1 + 1 + 1 + 1 + 1 + 1 + 1 + 4;  // kv_full, q_full[2], q_empty[2], do_full, do_empty, sdp_full, pt_ready, dq_full, dq_free, pa_ready, stage_free[4]
   static constexpr int DYN = BAR_OFF + NUM_BARS * 8 + 16;   // 231,528 B at D=128: no room for manual alignment slack
 };
 
@@ -374,6 +374,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* dq_full = bars + 9;
   uint64_t* dq_free = bars + 10;
   uint64_t* pa_ready = bars + 11;
+  uint64_t* stage_free = bars + 12;  // [4]: per lane quarter, the dQ staging (aliasing P^T / dS^T rows of that quarter) has been read by TMA
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
   float* s_lse = reinterpret_cast<float*>(smem + L::LSE_OFF);  // [2][128]
   float* s_delta = s_lse + 256;                                 // [2][128]
@@ -405,6 +406,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(sdp_full, 1);
     mbar_init(pt_ready, 16);
     mbar_init(pa_ready, 16);
+    for (int i = 0; i < 4; ++i) mbar_init(&stage_free[i], D / 32);  // the OUT_CHUNKS warps of a lane quarter
     mbar_init(dq_full, 1);
     mbar_init(dq_free, D / 8);   // (D/32 column chunks) x 4 lane quarters
     fence_mbar_init();
@@ -555,7 +557,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           nxt_dlt = delta[static_cast<int64_t>(h_n) * T + s0 + qi];
         }
       }
-      if (chunk < OUT_CHUNKS && quad == 0 && lane == 0) tma_store_wait_read<0>();  // previous pair's dQ staging has been read out
       asm volatile("bar.sync 1, 512;" ::: "memory");
       CPROF(8);
       const bool need_mask = (mt == nt) || (m0 + 128 > len) || (n0 + 128 > len);
@@ -564,9 +565,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_after();
       {
         const int c = chunk;  // this warp's 32 q columns
-        uint32_t sv[32], dv_[32];
+        uint32_t sv[32];
         tmem_ld_32x32b_x32(tST + lane_addr + c * 32, sv);
-        tmem_ld_32x32b_x32(tDP + lane_addr + c * 32, dv_);
         tmem_ld_wait();
         // ---- phase A: P^T = 2^(S^T * scale*log2e - lse*log2e)  -> smem; the MMA warp starts dV += P^T dO right away
         const float4* l4 = reinterpret_cast<const float4*>(lse2 + c * 32);
@@ -586,6 +586,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             if (qc < kv || qc >= len || kv >= len) pf[e] = 0.f;
           }
         }
+        // the previous pair's dQ staging lives in these P^T / dS^T rows: its TMA reduce must have finished READING them.
+        // Checked only now, after the exp work, so the reduction drains behind it instead of on the critical path.
+        if (chunk < OUT_CHUNKS) {
+          if (lane == 0) {
+            tma_store_wait_read<0>();
+            mbar_arrive(&stage_free[quad]);
+          }
+        }
+        mbar_wait(&stage_free[quad], p & 1);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           const int ch = c * 4 + q4;  // 16-byte chunk = 8 q columns; atom = ch / 8
@@ -599,6 +608,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(pa_ready);
         // ---- phase B: dS^T = P^T * (dP^T - delta) -> smem
+        uint32_t dv_[32];
+        tmem_ld_32x32b_x32(tDP + lane_addr + c * 32, dv_);
+        tmem_ld_wait();
         const float4* d4 = reinterpret_cast<const float4*>(dlt + c * 32);
 #pragma unroll
         for (int e4 = 0; e4 < 8; ++e4) {
@@ -641,9 +653,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int q4 = 0; q4 < 8; ++q4)
           *reinterpret_cast<uint4*>(stage + ((q4 ^ (r & 7)) << 4)) = make_uint4(qv[q4 * 4], qv[q4 * 4 + 1], qv[q4 * 4 + 2], qv[q4 * 4 + 3]);
         fence_proxy_async_smem();
-        asm volatile("bar.sync %0, 128;" ::"r"(2 + chunk) : "memory");  // the four lane-quarter warps of this chunk
-        if (quad == 0 && lane == 0) {
-          tma_reduce_add_2d(&tmDQ, smem + L::PT_OFF + chunk * 16384, h * D + chunk * 32, s0 + m0);
+        __syncwarp();
+        if (lane == 0) {  // one [32 rows x 32 floats] box per warp: no cross-warp barrier, 16 reductions in flight per CTA
+          tma_reduce_add_2d(&tmDQ, smem + L::PT_OFF + chunk * 16384 + quad * 4096, h * D + chunk * 32, s0 + m0 + quad * 32);
           tma_store_commit();
         }
       }
@@ -651,7 +663,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       h = h_n;
       mt = mt_n;
     }
-    if (chunk < OUT_CHUNKS && quad == 0 && lane == 0) tma_store_wait<0>();
+    if (chunk < OUT_CHUNKS && lane == 0) tma_store_wait<0>();
     // final dK (scaled) / dV rows; dq_full of the last pair covers every MMA of the CTA
     mbar_wait(dq_full, (n_pairs - 1) & 1);
     if (chunk < OUT_CHUNKS) {
@@ -712,7 +724,7 @@ static int attn_bwd_tc_launch(const void* q, const void* k, const void* v, const
   int rc;
   if ((rc = attn_delta_launch(o, dout, delta, ldo, lddo, Hq, D, T, st))) return rc;
   CUtensorMap tq, tk, tv, tdo, tdq;
-  if ((rc = make_tmap_2d_f32(&tdq, dq_acc, T, static_cast<uint64_t>(Hq) * D, static_cast<uint64_t>(Hq) * D, 32, 128))) return rc;
+  if ((rc = make_tmap_2d_f32(&tdq, dq_acc, T, static_cast<uint64_t>(Hq) * D, static_cast<uint64_t>(Hq) * D, 32, 32))) return rc;
   if ((rc = make_tmap_2d_bf16(&tq, q, T, static_cast<uint64_t>(Hq) * D, ldq, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tk, k, T, static_cast<uint64_t>(Hkv) * D, ldk, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tv, v, T, static_cast<uint64_t>(Hkv) * D, ldv, 64, 128))) return rc;
