@@ -380,15 +380,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   float* s_delta = s_lse + 256;                                 // [2][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int seq = blockIdx.z, hk = blockIdx.y, nt = blockIdx.x;
+  const int seq = blockIdx.z, hk = blockIdx.y;
   const int s0 = cu_seqlens[seq];
   const int len = cu_seqlens[seq + 1] - s0;
-  const int n0 = nt * 128;
-  if (n0 >= len) return;
   const int G = Hq / Hkv;
-  const int mt_end = (len + 127) / 128;
-  const int pairs_per_head = mt_end - nt;
-  const int n_pairs = G * pairs_per_head;
+  const int mt_end = (len + 127) / 128;  // kv / q tiles of this sequence
+  // Causal load balance: CTA x takes kv tile x (mt_end - x q tiles per head) AND kv tile mt_end-1-x (x+1 q tiles): every CTA of a
+  // sequence does the same number of (q tile, kv tile) pairs.
+  if (static_cast<int>(blockIdx.x) >= (mt_end + 1) / 2) return;
+  const int nt_pass[2] = {static_cast<int>(blockIdx.x), mt_end - 1 - static_cast<int>(blockIdx.x)};
+  const int n_pass = nt_pass[0] == nt_pass[1] ? 1 : 2;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -424,24 +425,34 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
-      mbar_arrive_expect_tx(kv_full, 2 * L::TILE);
+      int gp = 0;  // pairs issued so far over both passes (barrier parities / Q stages run on this global counter)
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int nt = nt_pass[pass], n0 = nt * 128;
+        const int pairs_per_head = mt_end - nt, n_pairs = G * pairs_per_head;
+        if (pass > 0) mbar_wait(dq_full, (gp - 1) & 1);  // every MMA of the previous pass (readers of K / V) has completed
+        mbar_arrive_expect_tx(kv_full, 2 * L::TILE);
 #pragma unroll
-      for (int a = 0; a < ATOMS; ++a) {
-        tma_load_2d(smem + L::K_OFF + a * 16384, &tmK, kv_full, hk * D + a * 64, s0 + n0);
-        tma_load_2d(smem + L::V_OFF + a * 16384, &tmV, kv_full, hk * D + a * 64, s0 + n0);
-      }
-      for (int p = 0; p < n_pairs; ++p) {
-        const int h = hk * G + p / pairs_per_head;
-        const int m0 = (nt + p % pairs_per_head) * 128;
-        const int st = p & 1;
-        mbar_wait(&q_empty[st], ((p >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&q_full[st], L::TILE);
+        for (int a = 0; a < ATOMS; ++a) {
+          tma_load_2d(smem + L::K_OFF + a * 16384, &tmK, kv_full, hk * D + a * 64, s0 + n0);
+          tma_load_2d(smem + L::V_OFF + a * 16384, &tmV, kv_full, hk * D + a * 64, s0 + n0);
+        }
+        int h = hk * G, mt = nt;
+        for (int p = 0; p < n_pairs; ++p, ++gp) {
+          const int m0 = mt * 128;
+          const int st = gp & 1;
+          mbar_wait(&q_empty[st], ((gp >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&q_full[st], L::TILE);
 #pragma unroll
-        for (int a = 0; a < ATOMS; ++a) tma_load_2d(smem + L::Q_OFF + st * L::TILE + a * 16384, &tmQ, &q_full[st], h * D + a * 64, s0 + m0);
-        mbar_wait(do_empty, (p & 1) ^ 1);
-        mbar_arrive_expect_tx(do_full, L::TILE);
+          for (int a = 0; a < ATOMS; ++a) tma_load_2d(smem + L::Q_OFF + st * L::TILE + a * 16384, &tmQ, &q_full[st], h * D + a * 64, s0 + m0);
+          mbar_wait(do_empty, (gp & 1) ^ 1);
+          mbar_arrive_expect_tx(do_full, L::TILE);
 #pragma unroll
-        for (int a = 0; a < ATOMS; ++a) tma_load_2d(smem + L::DO_OFF + a * 16384, &tmDO, do_full, h * D + a * 64, s0 + m0);
+          for (int a = 0; a < ATOMS; ++a) tma_load_2d(smem + L::DO_OFF + a * 16384, &tmDO, do_full, h * D + a * 64, s0 + m0);
+          if (++mt == mt_end) {
+            mt = nt;
+            ++h;
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -453,58 +464,62 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t k_base = smem_u32(smem + L::K_OFF), v_base = smem_u32(smem + L::V_OFF);
       const uint32_t do_base = smem_u32(smem + L::DO_OFF);
       const uint32_t pt_base = smem_u32(smem + L::PT_OFF), dst_base = smem_u32(smem + L::DST_OFF);
-      mbar_wait(kv_full, 0);
       PROF_DECL;
-      for (int p = 0; p < n_pairs; ++p) {
-        const int st = p & 1;
-        const uint32_t q_base = smem_u32(smem + L::Q_OFF + st * L::TILE);
-        // S^T (the compute warps finished loading S^T_{p-1} before pt_ready_{p-1}, which this thread has waited on)
-        mbar_wait(&q_full[st], (p >> 1) & 1);
-        PROF(0);
-        tc_fence_after();
+      int gp = 0;
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int n_pairs = G * (mt_end - nt_pass[pass]);
+        mbar_wait(kv_full, pass & 1);
+        for (int p = 0; p < n_pairs; ++p, ++gp) {
+          const int st = gp & 1;
+          const uint32_t q_base = smem_u32(smem + L::Q_OFF + st * L::TILE);
+          // S^T (the compute warps finished loading S^T of the previous pair before its pt_ready, which this thread has waited on)
+          mbar_wait(&q_full[st], (gp >> 1) & 1);
+          PROF(0);
+          tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
-          umma_bf16(tST, make_smem_desc_sw128(k_base + off, 16, 1024), make_smem_desc_sw128(q_base + off, 16, 1024), idesc_st, kk != 0);
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+            umma_bf16(tST, make_smem_desc_sw128(k_base + off, 16, 1024), make_smem_desc_sw128(q_base + off, 16, 1024), idesc_st, kk != 0);
+          }
+          // dP^T goes where the previous pair's dQ lives: wait until it has been read out
+          PROF(1);
+          mbar_wait(do_full, gp & 1);
+          PROF(2);
+          mbar_wait(dq_free, (gp & 1) ^ 1);
+          PROF(3);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+            umma_bf16(tDP, make_smem_desc_sw128(v_base + off, 16, 1024), make_smem_desc_sw128(do_base + off, 16, 1024), idesc_st, kk != 0);
+          }
+          umma_commit(sdp_full);
+          PROF(4);
+          mbar_wait(pa_ready, gp & 1);  // P^T is in smem (dS^T still being computed: dV overlaps it)
+          tc_fence_after();
+          // dV += P^T dO      A: P^T [kv x q] K-major (2 atoms of 64 q);  B: dO [q x d] MN-major.  p == 0 starts a fresh kv tile.
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16(tDV, make_smem_desc_sw128(pt_base + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                      make_smem_desc_sw128(do_base + kk * 2048, 16384, 1024), idesc_dkv, (p | kk) != 0);
+          umma_commit(do_empty);
+          mbar_wait(pt_ready, gp & 1);
+          PROF(5);
+          tc_fence_after();
+          // dK += dS^T Q
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16(tDK, make_smem_desc_sw128(dst_base + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                      make_smem_desc_sw128(q_base + kk * 2048, 16384, 1024), idesc_dkv, (p | kk) != 0);
+          umma_commit(&q_empty[st]);
+          // dQ = dS K         A: dS from the dS^T tile read MN-major (M = q contiguous, K = kv rows);  B: K [kv x d] MN-major
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16(tDP, make_smem_desc_sw128(dst_base + kk * 2048, 16384, 1024), make_smem_desc_sw128(k_base + kk * 2048, 16384, 1024),
+                      idesc_dq, kk != 0);
+          umma_commit(dq_full);
+          PROF(6);
         }
-        // dP^T goes where dQ_{p-1} lives: wait until it has been read out
-        PROF(1);
-        mbar_wait(do_full, p & 1);
-        PROF(2);
-        mbar_wait(dq_free, (p & 1) ^ 1);
-        PROF(3);
-        tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
-          umma_bf16(tDP, make_smem_desc_sw128(v_base + off, 16, 1024), make_smem_desc_sw128(do_base + off, 16, 1024), idesc_st, kk != 0);
-        }
-        umma_commit(sdp_full);
-        PROF(4);
-        mbar_wait(pa_ready, p & 1);   // P^T is in smem (dS^T still being computed: dV overlaps it)
-        tc_fence_after();
-        // dV += P^T dO      A: P^T [kv x q] K-major (2 atoms of 64 q);  B: dO [q x d] MN-major
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_bf16(tDV, make_smem_desc_sw128(pt_base + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                    make_smem_desc_sw128(do_base + kk * 2048, 16384, 1024), idesc_dkv, (p | kk) != 0);
-        umma_commit(do_empty);
-        mbar_wait(pt_ready, p & 1);
-        PROF(5);
-        tc_fence_after();
-        // dK += dS^T Q
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_bf16(tDK, make_smem_desc_sw128(dst_base + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                    make_smem_desc_sw128(q_base + kk * 2048, 16384, 1024), idesc_dkv, (p | kk) != 0);
-        umma_commit(&q_empty[st]);
-        // dQ = dS K         A: dS from the dS^T tile read MN-major (M = q contiguous, K = kv rows);  B: K [kv x d] MN-major
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_bf16(tDP, make_smem_desc_sw128(dst_base + kk * 2048, 16384, 1024), make_smem_desc_sw128(k_base + kk * 2048, 16384, 1024),
-                    idesc_dq, kk != 0);
-        umma_commit(dq_full);
-        PROF(6);
       }
     }
   } else {
@@ -516,7 +531,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int chunk = cw >> 2;       // 0..3
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    const int kv = n0 + r;
     const int ct = threadIdx.x - 64;  // 0..511; the first 128 stage the per-q statistics
     constexpr float LOG2E = 1.4426950408889634f;
     constexpr int OUT_CHUNKS = D / 32;  // column chunks of the dQ / dK / dV tiles
@@ -528,6 +542,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #else
 #define CPROF(slot)
 #endif
+    int gp = 0;  // global pair counter over both passes (barrier parities)
+    for (int pass = 0; pass < n_pass; ++pass) {
+    const int nt = nt_pass[pass], n0 = nt * 128;
+    const int n_pairs = G * (mt_end - nt);
+    const int kv = n0 + r;
     // per-q statistics (lse*log2e, delta) of the NEXT pair are fetched one pair ahead into registers of the first 128 threads
     float nxt_lse = 0.f, nxt_dlt = 0.f;
     if (ct < 128) {
@@ -538,15 +557,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
     int h = hk * G, mt = nt;
-    for (int p = 0; p < n_pairs; ++p) {
+    for (int p = 0; p < n_pairs; ++p, ++gp) {
       const int m0 = mt * 128;
       int h_n = h, mt_n = mt + 1;
       if (mt_n == mt_end) {
         mt_n = nt;
         ++h_n;
       }
-      float* lse2 = s_lse + (p & 1) * 128;
-      float* dlt = s_delta + (p & 1) * 128;
+      float* lse2 = s_lse + (gp & 1) * 128;
+      float* dlt = s_delta + (gp & 1) * 128;
       if (ct < 128) {
         lse2[ct] = nxt_lse;
         dlt[ct] = nxt_dlt;
@@ -560,7 +579,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       asm volatile("bar.sync 1, 512;" ::: "memory");
       CPROF(8);
       const bool need_mask = (mt == nt) || (m0 + 128 > len) || (n0 + 128 > len);
-      mbar_wait(sdp_full, p & 1);
+      mbar_wait(sdp_full, gp & 1);
       CPROF(9);
       tc_fence_after();
       {
@@ -594,7 +613,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_arrive(&stage_free[quad]);
           }
         }
-        mbar_wait(&stage_free[quad], p & 1);
+        mbar_wait(&stage_free[quad], gp & 1);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           const int ch = c * 4 + q4;  // 16-byte chunk = 8 q columns; atom = ch / 8
@@ -638,7 +657,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // warps that own a column chunk copy it TMEM -> registers -> swizzled fp32 staging (the now idle P^T/dS^T buffers) and
       // ONE thread per chunk issues a TMA reduce-add of the [128 x 32] fp32 box into the dq accumulator: 4 bulk L2 reductions per
       // pair instead of 4096 vector atomics.  Rows past the sequence end carry exact zeros (their dS is masked).
-      mbar_wait(dq_full, p & 1);
+      mbar_wait(dq_full, gp & 1);
       CPROF(11);
       if (chunk < OUT_CHUNKS) {
         tc_fence_after();
@@ -664,8 +683,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mt = mt_n;
     }
     if (chunk < OUT_CHUNKS && lane == 0) tma_store_wait<0>();
-    // final dK (scaled) / dV rows; dq_full of the last pair covers every MMA of the CTA
-    mbar_wait(dq_full, (n_pairs - 1) & 1);
+    // dK (scaled) / dV rows of this kv tile; dq_full of the pass's last pair covers every MMA of the pass.  The next pass's first
+    // dV / dK MMAs (accumulate = 0) are issued only after these warps have moved on to its first pair (pa_ready), i.e. after this read.
+    mbar_wait(dq_full, (gp - 1) & 1);
     if (chunk < OUT_CHUNKS) {
       tc_fence_after();
       const bool valid = kv < len;  // tcgen05.ld is warp-collective: every lane loads, only valid rows store
@@ -693,6 +713,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       tc_fence_before();
     }
+    }  // pass
   }
   __syncthreads();
   if (warp == 1) {
@@ -729,7 +750,7 @@ static int attn_bwd_tc_launch(const void* q, const void* k, const void* v, const
   if ((rc = make_tmap_2d_bf16(&tk, k, T, static_cast<uint64_t>(Hkv) * D, ldk, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tv, v, T, static_cast<uint64_t>(Hkv) * D, ldv, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tdo, dout, T, static_cast<uint64_t>(Hq) * D, lddo, 64, 128))) return rc;
-  dim3 grid((max_len + 127) / 128, Hkv, nseq);
+  dim3 grid(((max_len + 127) / 128 + 1) / 2, Hkv, nseq);
   kern<<<grid, 576, L::DYN, st>>>(tq, tk, tv, tdo, tdq, lse, delta, static_cast<__nv_bfloat16*>(dk), static_cast<__nv_bfloat16*>(dv), cu,
                                   lddk, lddv, Hq, Hkv, T, scale, scale * 1.4426950408889634f);
   B200_CHECK_LAUNCH("attn_bwd_tc");
@@ -740,7 +761,7 @@ static int attn_bwd_tc_launch(const void* q, const void* k, const void* v, const
     cudaMemcpyFromSymbol(h, g_attn_prof, sizeof(h));
     static const char* names[] = {"mma:wait q_full", "mma:issue S^T", "mma:wait do_full", "mma:wait dq_free", "mma:issue dP^T", "mma:wait pt_ready",
                                   "mma:issue dV,dK,dQ", "", "cmp:stats+bar", "cmp:wait sdp_full", "cmp:compute+store", "cmp:wait dq_full", "cmp:dq readout"};
-    const int npairs = (Hq / Hkv) * ((max_len + 127) / 128);
+    const int npairs = (Hq / Hkv) * ((max_len + 127) / 128 + 1);
     for (int i = 0; i < 13; ++i) if (names[i][0]) fprintf(stderr, "ATTN_PROF %-22s %8.0f cycles/pair\n", names[i], double(h[i]) / npairs);
     unsigned long long z[32] = {0};
     cudaMemcpyToSymbol(g_attn_prof, z, sizeof(z));

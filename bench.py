@@ -127,7 +127,21 @@ def run_cpu_reference(steps, warmup, budget_s=150.0, quiet=False):
 
 
 # ------------------------------------------------------------------------------------------------ our arm (GPU)
+def _claim_stdout():
+    """The driver parses ONE JSON line from stdout; libraries (NCCL prints its version banner there) must not interleave.
+    fd 1 is pointed at stderr for the whole run and the JSON line is written to the saved descriptor at the end."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _emit(saved_fd, line):
+    os.write(saved_fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    saved_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -152,7 +166,7 @@ def main():
                 "config": {"workload": "llama3_8b_sft_seq4096_b1_per_gpu", "note": "CPU reference arm runs a bounded sample, see cpu_baseline.sample"},
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        _emit(saved_stdout, line)
         return 0
 
     import torch
@@ -287,7 +301,7 @@ def main():
         line["profile_mode"] = True
     if not args.no_cpu_baseline and not args.profile and world == 1:
         line["cpu_baseline"] = run_cpu_reference(steps=3, warmup=1, budget_s=40.0)
-    print(json.dumps(line), flush=True)
+    _emit(saved_stdout, line)
     if world > 1:
         dist.destroy_process_group()
     return 0
