@@ -22,7 +22,7 @@ if bad.any():
     rows = bad.any(1).nonzero().flatten(); cols = bad.any(0).nonzero().flatten()
     print("  bad rows: n=%%d min=%%d max=%%d ; bad cols: n=%%d min=%%d max=%%d" %% (len(rows), rows.min(), rows.max(), len(cols), cols.min(), cols.max()))
 '''
-cases = [(k, *s) for k in (0, 1, 2) for s in [(128, 256, 64), (128, 256, 256), (256, 512, 128), (128, 128, 64), (384, 320, 192), (4096, 4096, 4096)]]
+cases = [(k, *s) for k in (0, 1, 2) for s in [(128, 256, 64), (128, 192, 64), (256, 512, 128), (128, 128, 64), (384, 320, 192), (512, 960, 320), (4096, 6144, 4096)]]
 fails = 0
 for c in cases:
     t0 = time.time()
@@ -45,7 +45,12 @@ if "--bench" in sys.argv and fails == 0:
                             (2, (6144, 4096, 4096)), (2, (28672, 4096, 4096)), (2, (4096, 14336, 4096)), (0, (8192, 8192, 8192))]:
         a = torch.randn((M, K) if kind != 2 else (K, M), device="cuda").bfloat16(); b = torch.randn((N, K) if kind == 0 else (K, N), device="cuda").bfloat16()
         out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-        for name, fn in [("tcgen05", lambda: ops.gemm(kind, a, b, out=out)), ("cublasLt", lambda: ops.gemm_cublaslt(kind, a, b, out=out))]:
+        def mk(bn):
+            def f():
+                ops.set_option("gemm_bn", bn); ops.gemm(kind, a, b, out=out); ops.set_option("gemm_bn", 0)
+            return f
+        for name, fn in [("tcgen05", lambda: ops.gemm(kind, a, b, out=out)), ("tc_bn256", mk(256)), ("tc_bn192", mk(192)), ("tc_bn128", mk(128)),
+                         ("cublasLt", lambda: ops.gemm_cublaslt(kind, a, b, out=out))]:
             for _ in range(3): fn()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize(); e0.record()
