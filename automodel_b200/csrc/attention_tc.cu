@@ -348,7 +348,7 @@ struct AttnBwdSmem {
   static constexpr int DST_OFF = PT_OFF + PT_BYTES;
   static constexpr int LSE_OFF = DST_OFF + PT_BYTES;          // float [2][128] lse*log2e, then [2][128] delta
   static constexpr int BAR_OFF = LSE_OFF + 4 * 128 * 4;
-  static constexpr int NUM_BARS = 1 + 2 + 2 + 1 + 1 + 1 + 1 + 1 + 1 + 1 + 4;  // kv_full, q_full[2], q_empty[2], do_full, do_empty, sdp_full, pt_ready, dq_full, dq_free, pa_ready, stage_free[4]
+  static constexpr int NUM_BARS = 1 + 2 + 2 + 1 + 1 + 1 + 1 + 1 + 1 + 1 + 4 + 1;  // kv_full, q_full[2], q_empty[2], do_full, do_empty, sdp_full, pt_ready, dq_full, dq_free, pa_ready, stage_free[4]
   static constexpr int DYN = BAR_OFF + NUM_BARS * 8 + 16;   // 231,528 B at D=128: no room for manual alignment slack
 };
 
@@ -374,6 +374,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* dq_full = bars + 9;
   uint64_t* dq_free = bars + 10;
   uint64_t* pa_ready = bars + 11;
+  uint64_t* kv_free = bars + 16;     // every MMA of a pass (readers of the K / V tiles) has completed
   uint64_t* stage_free = bars + 12;  // [4]: per lane quarter, the dQ staging (aliasing P^T / dS^T rows of that quarter) has been read by TMA
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
   float* s_lse = reinterpret_cast<float*>(smem + L::LSE_OFF);  // [2][128]
@@ -407,6 +408,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(sdp_full, 1);
     mbar_init(pt_ready, 16);
     mbar_init(pa_ready, 16);
+    mbar_init(kv_free, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&stage_free[i], D / 32);  // the OUT_CHUNKS warps of a lane quarter
     mbar_init(dq_full, 1);
     mbar_init(dq_free, D / 8);   // (D/32 column chunks) x 4 lane quarters
@@ -429,7 +431,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int pass = 0; pass < n_pass; ++pass) {
         const int nt = nt_pass[pass], n0 = nt * 128;
         const int pairs_per_head = mt_end - nt, n_pairs = G * pairs_per_head;
-        if (pass > 0) mbar_wait(dq_full, (gp - 1) & 1);  // every MMA of the previous pass (readers of K / V) has completed
+        // every MMA of the previous pass (readers of K / V) has completed.  A dedicated once-per-pass barrier: this thread can be
+        // two pairs ahead of the MMAs, so the per-pair dq_full parity would alias.
+        if (pass > 0) mbar_wait(kv_free, (pass - 1) & 1);
         mbar_arrive_expect_tx(kv_full, 2 * L::TILE);
 #pragma unroll
         for (int a = 0; a < ATOMS; ++a) {
@@ -520,6 +524,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           umma_commit(dq_full);
           PROF(6);
         }
+        umma_commit(kv_free);
       }
     }
   } else {

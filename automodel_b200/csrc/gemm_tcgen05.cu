@@ -389,21 +389,9 @@ int gemm_bf16_tcgen05(int kind, const void* A, int lda, const void* B, int ldb, 
   if (M <= 0 || N <= 0 || K <= 0) return set_error(B200_ERR_ARG, "gemm: empty problem %dx%dx%d", M, N, K);
   if ((flags & GEMM_FLAG_RESIDUAL) && !R) return set_error(B200_ERR_ARG, "gemm: residual flag without R");
   if (group_m <= 0) group_m = 8;
-  // Tile-width choice against wave quantisation of the persistent grid: time ~ waves(BN) * BN * per-tile inefficiency(BN).
-  // e.g. 4096 x 6144: 768 tiles of 128x256 = 5.19 waves -> 6 (86 %); 1024 tiles of 128x192 = 6.9 waves -> 7 of 0.75 the work (99 %).
-  const int sms = max_ctas > 0 && max_ctas < num_sms() ? max_ctas : num_sms();
-  const int tiles_m = (M + BM - 1) / BM;
-  auto cost = [&](int bn, double penalty) {
-    const long tiles = static_cast<long>(tiles_m) * ((N + bn - 1) / bn);
-    return static_cast<double>((tiles + sms - 1) / sms) * bn * penalty;
-  };
-  int bn = 256;
-  double best = cost(256, 1.0);
-  if (N >= 192 && cost(192, 1.03) < best) {
-    best = cost(192, 1.03);
-    bn = 192;
-  }
-  if (cost(128, 1.12) < best) bn = 128;
+  // 128x256 tiles whenever N allows (measured: 128x192 / 128x128 tiles lose more in per-tile efficiency than they win back in
+  // wave quantisation on every Llama-3-8B shape, profiles/r1_gemm_tile_sweep.md)
+  int bn = ((N % 256 == 0) || N >= 1024) ? 256 : 128;
   if (forced_bn == 128 || forced_bn == 192 || forced_bn == 256) bn = forced_bn;
   if (bn == 256) return gemm_dispatch_kind<256, 4>(kind, A, lda, B, ldb, C, ldc, R, ldr, M, N, K, flags, group_m, max_ctas, stream);
   if (bn == 192) return gemm_dispatch_kind<192, 4>(kind, A, lda, B, ldb, C, ldc, R, ldr, M, N, K, flags, group_m, max_ctas, stream);
