@@ -109,6 +109,15 @@ class ShardedLlamaEngine:
             self.rank = dist.get_rank(process_group)
         else:
             self.world, self.rank = 1, 0
+        # While NCCL kernels (reduce-scatter / all-gather on the side stream) occupy SMs, a persistent GEMM with one CTA per SM would
+        # leave its last CTAs waiting for an SM and double its makespan: with N > 1 the GEMMs run on (SMs - comm_sms) CTAs.
+        self.comm_sms = 0
+        if self.world > 1 and self.device.type == "cuda":
+            import os
+            self.comm_sms = int(os.environ.get("B200_COMM_SMS", "8"))
+        self.gemm_ctas = 0  # 0 = one CTA per SM
+        if self.comm_sms > 0:
+            self.gemm_ctas = torch.cuda.get_device_properties(self.device).multi_processor_count - self.comm_sms
         self.units: List[UnitLayout] = build_layout(d, self.world)
         self.n_params = total_params(self.units)
         self.max_tokens = max_tokens
@@ -330,6 +339,11 @@ class ShardedLlamaEngine:
         self.loss_dev; parameter gradients (= or +=) land in the flat gradient buffers; on the last micro-batch each unit's
         gradients are reduce-scattered as soon as its backward is done."""
         ops, d, A, tmp = self.ops, self.dims, self.act, self.tmp
+        ctas = self.gemm_ctas
+
+        def G(*a, **k):
+            return ops.gemm(*a, max_ctas=ctas, **k)
+
         k, T, nseq, max_len = staged if staged is not None else self._stage_inputs(input_ids, labels, position_ids)
         devb = self._in_dev[k]
         ids, lab, pos, cu = devb[0:T], devb[T:2 * T], devb[2 * T:3 * T], devb[3 * T:3 * T + nseq + 1]
@@ -349,28 +363,28 @@ class ShardedLlamaEngine:
             x1 = sl(A["x1"][l]); qkv = sl(A["qkv"][l]); o2 = sl(A["o2"][l]); h1 = sl(A["h1"][l])
             x2 = sl(A["x2"][l]); gu = sl(A["gu"][l]); a = sl(A["a"][l])
             ops.rmsnorm_fwd(h, W["n1"], d.eps, out=x1, rstd=sl(A["rstd1"][l]))
-            ops.gemm(ops.NT, x1, W["qkv"], out=qkv)
+            G(ops.NT, x1, W["qkv"], out=qkv)
             ops.rope_(qkv, self.cos, self.sin, pos, Hq + Hkv, D)
             ops.attn_fwd(qkv[:, :qc], qkv[:, qc:qc + kc], qkv[:, qc + kc:], cu, max_len, Hq, Hkv, D, out=o2, lse=A["lse"][l])
-            ops.gemm(ops.NT, o2, W["o"], out=h1, residual=h, round_before_add=rba)
+            G(ops.NT, o2, W["o"], out=h1, residual=h, round_before_add=rba)
             ops.rmsnorm_fwd(h1, W["n2"], d.eps, out=x2, rstd=sl(A["rstd2"][l]))
-            ops.gemm(ops.NT, x2, W["gu"], out=gu)
+            G(ops.NT, x2, W["gu"], out=gu)
             ops.swiglu_fwd(gu, out=a)
-            ops.gemm(ops.NT, a, W["down"], out=sl(A["h"][l + 1]), residual=h1, round_before_add=rba)
+            G(ops.NT, a, W["down"], out=sl(A["h"][l + 1]), residual=h1, round_before_add=rba)
         self._wait_params(1 + L)
         hL = sl(A["h"][L])
         xf = sl(self.xf)
         ops.rmsnorm_fwd(hL, self.P["model.norm.weight"], d.eps, out=xf, rstd=sl(self.rstdf))
         logits = sl(self.logits)
-        ops.gemm(ops.NT, xf, self.P["lm_head.weight"], out=logits)
+        G(ops.NT, xf, self.P["lm_head.weight"], out=logits)
         # fused CE: loss accumulates on the device, logits become dlogits in place (components/loss/masked_ce.py:73-89)
         ops.ce_fwd_bwd_(logits, lab, num_label_tokens, self.loss_dev, accumulate=True, row_loss=sl(self.row_loss))
 
         # ---------------- backward
         head_ui = 1 + L
-        ops.gemm(ops.TN, logits, xf, out=self.G["lm_head.weight"], residual=self.G["lm_head.weight"] if acc else None)
+        G(ops.TN, logits, xf, out=self.G["lm_head.weight"], residual=self.G["lm_head.weight"] if acc else None)
         dxf = sl(tmp["dxf"])
-        ops.gemm(ops.NN, logits, self.P["lm_head.weight"], out=dxf)
+        G(ops.NN, logits, self.P["lm_head.weight"], out=dxf)
         dh = sl(tmp["dh_a"]); dh_next = sl(tmp["dh_b"])
         ops.rmsnorm_bwd(dxf, hL, self.P["model.norm.weight"], sl(self.rstdf), dx=dh, dw=self.G["model.norm.weight"],
                         accumulate_dw=acc, workspace=self.norm_ws)
@@ -382,22 +396,22 @@ class ShardedLlamaEngine:
             x2 = sl(A["x2"][l]); gu = sl(A["gu"][l]); a = sl(A["a"][l])
             da = sl(tmp["da"]); dgu = sl(tmp["dgu"]); dx = sl(tmp["dx"]); do2 = sl(tmp["do2"]); dqkv = sl(tmp["dqkv"])
             # MLP
-            ops.gemm(ops.TN, dh, a, out=W["d_down"], residual=W["d_down"] if acc else None)
-            ops.gemm(ops.NN, dh, W["down"], out=da)
+            G(ops.TN, dh, a, out=W["d_down"], residual=W["d_down"] if acc else None)
+            G(ops.NN, dh, W["down"], out=da)
             ops.swiglu_bwd(da, gu, out=dgu)
-            ops.gemm(ops.TN, dgu, x2, out=W["d_gu"], residual=W["d_gu"] if acc else None)
-            ops.gemm(ops.NN, dgu, W["gu"], out=dx)
+            G(ops.TN, dgu, x2, out=W["d_gu"], residual=W["d_gu"] if acc else None)
+            G(ops.NN, dgu, W["gu"], out=dx)
             # dh1 = dh + rmsnorm'(dx2)
             ops.rmsnorm_bwd(dx, h1, W["n2"], sl(A["rstd2"][l]), dres=dh, dx=dh_next, dw=W["d_n2"], accumulate_dw=acc, workspace=self.norm_ws)
             dh, dh_next = dh_next, dh
             # attention
-            ops.gemm(ops.TN, dh, o2, out=W["d_o"], residual=W["d_o"] if acc else None)
-            ops.gemm(ops.NN, dh, W["o"], out=do2)
+            G(ops.TN, dh, o2, out=W["d_o"], residual=W["d_o"] if acc else None)
+            G(ops.NN, dh, W["o"], out=do2)
             ops.attn_bwd(qkv[:, :qc], qkv[:, qc:qc + kc], qkv[:, qc + kc:], o2, do2, A["lse"][l], cu, max_len, Hq, Hkv, D,
                          dqkv[:, :qc], dqkv[:, qc:qc + kc], dqkv[:, qc + kc:], workspace=self.attn_ws)
             ops.rope_(dqkv, self.cos, self.sin, pos, Hq + Hkv, D, backward=True)
-            ops.gemm(ops.TN, dqkv, x1, out=W["d_qkv"], residual=W["d_qkv"] if acc else None)
-            ops.gemm(ops.NN, dqkv, W["qkv"], out=dx)
+            G(ops.TN, dqkv, x1, out=W["d_qkv"], residual=W["d_qkv"] if acc else None)
+            G(ops.NN, dqkv, W["qkv"], out=dx)
             ops.rmsnorm_bwd(dx, h, W["n1"], sl(A["rstd1"][l]), dres=dh, dx=dh_next, dw=W["d_n1"], accumulate_dw=acc, workspace=self.norm_ws)
             dh, dh_next = dh_next, dh
             if last_micro:
