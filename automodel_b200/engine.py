@@ -109,12 +109,11 @@ class ShardedLlamaEngine:
             self.rank = dist.get_rank(process_group)
         else:
             self.world, self.rank = 1, 0
-        # While NCCL kernels (reduce-scatter / all-gather on the side stream) occupy SMs, a persistent GEMM with one CTA per SM would
-        # leave its last CTAs waiting for an SM and double its makespan: with N > 1 the GEMMs run on (SMs - comm_sms) CTAs.
+        # Optional: run the persistent GEMMs on (SMs - comm_sms) CTAs while NCCL kernels overlap them (B200_COMM_SMS, default 0).
         self.comm_sms = 0
         if self.world > 1 and self.device.type == "cuda":
             import os
-            self.comm_sms = int(os.environ.get("B200_COMM_SMS", "8"))
+            self.comm_sms = int(os.environ.get("B200_COMM_SMS", "0"))  # measured at N=2 (profiles/r1_n2_comm_sms.md): 0 is best
         self.gemm_ctas = 0  # 0 = one CTA per SM
         if self.comm_sms > 0:
             self.gemm_ctas = torch.cuda.get_device_properties(self.device).multi_processor_count - self.comm_sms

@@ -180,8 +180,6 @@ def main():
     ops.device_check()
     pg = None
     if world > 1:
-        # NCCL's reduce-scatter / all-gather overlap the GEMMs: keep them on few SMs (the engine leaves B200_COMM_SMS free)
-        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("B200_COMM_SMS", "8"))
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
     cfg = dict(LLAMA3_8B)
