@@ -33,6 +33,14 @@ SIGNATURES = {
     "b200_sumsq_bf16": (_i, [_vp, _i64, _vp, _vp, _i, _vp]),
     "b200_adamw_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _vp, _i, _vp]),
     "b200_add_inplace_bf16": (_i, [_vp, _vp, _i64, _vp]),
+    "b200_mem_alloc": (_i, [C.POINTER(_vp), _sz]),
+    "b200_mem_free": (_i, [_vp]),
+    "b200_ipc_export": (_i, [_vp, _vp]),
+    "b200_ipc_import": (_i, [_vp, C.POINTER(_vp)]),
+    "b200_ipc_close": (_i, [_vp]),
+    "b200_copy_async": (_i, [_vp, _vp, _sz, _vp]),
+    "b200_reduce_scatter_pull_workspace_floats": (_i, []),
+    "b200_reduce_scatter_pull_bf16": (_i, [_vp, C.POINTER(_vp), _i, _i64, _vp, _i, _vp, _i, _vp]),
 }
 
 

@@ -47,6 +47,15 @@ int attn_fwd_tc(const void*, const void*, const void*, void*, float*, const int*
 int attn_bwd_tc(const void*, const void*, const void*, const void*, const void*, const float*, void*, void*, void*, void*, const int*, int,
                 int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, int, int, float, cudaStream_t);
 
+int mem_alloc(void**, size_t);
+int mem_free(void*);
+int ipc_export(void*, void*);
+int ipc_import(const void*, void**);
+int ipc_close(void*);
+int copy_async(void*, const void*, size_t, cudaStream_t);
+int reduce_scatter_pull_workspace_floats();
+int reduce_scatter_pull_bf16(void*, const void* const*, int, int64_t, float*, int, float*, int, cudaStream_t);
+
 // debug option: 1 (default) = tcgen05/TMEM attention, 0 = the mma.sync v1 kernels (kept for bisecting only)
 static int g_attn_impl = 1;
 extern int forced_bn;
@@ -190,5 +199,17 @@ int b200_adamw_step(void* p, const void* g, void* m, void* v, float* master, int
   return adamw_step(p, g, m, v, master, n, lr, beta1, beta2, eps, weight_decay, step, max_grad_norm, grad_norm_sq, mode, S(stream));
 }
 int b200_add_inplace_bf16(void* dst, const void* src, int64_t n, b200_stream_t stream) { return add_inplace_bf16(dst, src, n, S(stream)); }
+
+int b200_mem_alloc(void** ptr, size_t bytes) { return mem_alloc(ptr, bytes); }
+int b200_mem_free(void* ptr) { return mem_free(ptr); }
+int b200_ipc_export(void* ptr, void* handle64) { return ipc_export(ptr, handle64); }
+int b200_ipc_import(const void* handle64, void** ptr) { return ipc_import(handle64, ptr); }
+int b200_ipc_close(void* ptr) { return ipc_close(ptr); }
+int b200_copy_async(void* dst, const void* src, size_t bytes, b200_stream_t stream) { return copy_async(dst, src, bytes, S(stream)); }
+int b200_reduce_scatter_pull_workspace_floats(void) { return reduce_scatter_pull_workspace_floats(); }
+int b200_reduce_scatter_pull_bf16(void* dst, const void* const* srcs, int nsrc, int64_t n, float* norm_sq, int accumulate_norm,
+                                  float* workspace, int ctas, b200_stream_t stream) {
+  return reduce_scatter_pull_bf16(dst, srcs, nsrc, n, norm_sq, accumulate_norm, workspace, ctas, S(stream));
+}
 
 }  // extern "C"

@@ -128,8 +128,25 @@ class ShardedLlamaEngine:
         bf, dev = torch.bfloat16, self.device
 
         # ---- persistent flat storage
-        self.p_full = [torch.zeros(u.padded, dtype=bf, device=dev) for u in self.units]   # unsharded params (shard lives inside)
-        self.g_full = [torch.zeros(u.padded, dtype=bf, device=dev) for u in self.units]   # unsharded grads (RS in place)
+        self.peer = None
+        import os as _os
+        if self.world > 1 and dev.type == "cuda" and _os.environ.get("B200_PEER_COMM", "1") != "0":
+            # NVLink peer-memory data path (csrc/comm.cu): parameters and gradients of all units live in two IPC-exported slabs
+            from .peer import Slab, PeerTable
+            offs, tot = [], 0
+            for u in self.units:
+                offs.append(tot)
+                tot += u.padded
+            self._unit_off = offs
+            self._p_slab, self._g_slab = Slab(tot, dev), Slab(tot, dev)
+            self.p_full = [self._p_slab.tensor[o:o + u.padded] for o, u in zip(offs, self.units)]
+            self.g_full = [self._g_slab.tensor[o:o + u.padded] for o, u in zip(offs, self.units)]
+            self.peer = (PeerTable(self._p_slab, process_group), PeerTable(self._g_slab, process_group))
+            self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+            self._rs_started = False
+        else:
+            self.p_full = [torch.zeros(u.padded, dtype=bf, device=dev) for u in self.units]   # unsharded params (shard lives inside)
+            self.g_full = [torch.zeros(u.padded, dtype=bf, device=dev) for u in self.units]   # unsharded grads (RS in place)
         self.m = [torch.zeros(u.padded // self.world, dtype=bf, device=dev) for u in self.units]
         self.v = [torch.zeros(u.padded // self.world, dtype=bf, device=dev) for u in self.units]
         self.master = [torch.zeros(u.padded // self.world, dtype=torch.float32, device=dev) for u in self.units] if master_weights else None
@@ -263,7 +280,23 @@ class ShardedLlamaEngine:
         st = self.streams
         ev = st.event()
         st.record(ev)                       # shard update (AdamW) issued on the compute stream
-        if st.cuda:
+        if st.cuda and self.peer is not None:
+            # copy-engine push of the updated shard into every peer's parameter buffer (zero SMs), then a 4-byte all-reduce as the
+            # "everybody's pushes have landed" flag (stream-ordered behind the copies on every rank)
+            a, b = self.units[ui].shard_range(self.rank, self.world)
+            off = (self._unit_off[ui] + a) * 2
+            tab = self.peer[0]
+            with torch.cuda.stream(st.comm):
+                st.wait(ev, st.comm)
+                cs = st.comm.cuda_stream
+                for k in range(1, self.world):
+                    j = (self.rank + k) % self.world
+                    self.ops.copy_async(tab.base[j] + off, tab.base[self.rank] + off, (b - a) * 2, cs)
+                dist.all_reduce(self._flag, group=self.pg)
+                done = st.event()
+                st.record(done, st.comm)
+                self.ev_ag[ui] = done
+        elif st.cuda:
             with torch.cuda.stream(st.comm):
                 st.wait(ev, st.comm)
                 dist.all_gather_into_tensor(self.p_full[ui], self.shard(self.p_full, ui), group=self.pg)
@@ -280,7 +313,22 @@ class ShardedLlamaEngine:
         st = self.streams
         ev = st.event()
         st.record(ev)                       # this unit's gradients are complete on the compute stream
-        if st.cuda:
+        if st.cuda and self.peer is not None:
+            # 4-byte all-reduce = "unit ui's gradients are complete on every rank"; then ONE kernel pulls this rank's slice from all
+            # peers over NVLink, reduces in fp32, writes the bf16 shard in place and accumulates the shard's sum of squares.
+            a, b = self.units[ui].shard_range(self.rank, self.world)
+            off = (self._unit_off[ui] + a) * 2
+            tab = self.peer[1]
+            with torch.cuda.stream(st.comm):
+                st.wait(ev, st.comm)
+                dist.all_reduce(self._flag, group=self.pg)
+                srcs = [tab.base[self.rank] + off] + [tab.base[(self.rank + k) % self.world] + off for k in range(1, self.world)]
+                self.ops.reduce_scatter_pull_(srcs[0], srcs, b - a, self.norm_sq, self._rs_started, self.device, stream=st.comm.cuda_stream)
+                self._rs_started = True
+                done = st.event()
+                st.record(done, st.comm)
+                self.ev_rs[ui] = done
+        elif st.cuda:
             with torch.cuda.stream(st.comm):
                 st.wait(ev, st.comm)
                 dist.reduce_scatter_tensor(self.shard(self.g_full, ui), self.g_full[ui], op=dist.ReduceOp.SUM, group=self.pg)
@@ -431,11 +479,15 @@ class ShardedLlamaEngine:
             self.lr = lr
         self.step_count += 1
         nu = len(self.units)
+        fused_norm = self.peer is not None and getattr(self, "_rs_started", False)
         for ui in range(nu):
             if self.ev_rs[ui] is not None:
                 self.streams.wait(self.ev_rs[ui])
                 self.ev_rs[ui] = None
-            ops.sumsq_(self.shard(self.g_full, ui), self.norm_sq, accumulate=ui > 0)
+            if not fused_norm:  # the pull kernel of the peer path already accumulated the shard's sum of squares
+                ops.sumsq_(self.shard(self.g_full, ui), self.norm_sq, accumulate=ui > 0)
+        if fused_norm:
+            self._rs_started = False
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.norm_sq, op=dist.ReduceOp.SUM, group=self.pg)

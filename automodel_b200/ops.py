@@ -236,3 +236,23 @@ def add_(dst, src):
     check(lib().b200_add_inplace_bf16(dst.data_ptr(), src.data_ptr(), dst.numel(), _st()), "b200_add_inplace_bf16")
     _count(1)
     return dst
+
+
+def copy_async(dst_ptr, src_ptr, nbytes, stream=None):
+    """Copy-engine copy between raw device pointers (peer-to-peer over NVLink when they live on different GPUs)."""
+    check(lib().b200_copy_async(dst_ptr, src_ptr, nbytes, stream if stream is not None else _st()), "b200_copy_async")
+
+
+_rs_ws = {}
+
+
+def reduce_scatter_pull_(dst_ptr, src_ptrs, n, norm_sq, accumulate_norm, device, ctas=32, stream=None):
+    """dst[i] = bf16(sum_j src_j[i]) (fp32 accumulate, source order), norm_sq (=|+=) sum of squares of the result."""
+    import ctypes as C
+    ws = _rs_ws.get(device)
+    if ws is None:
+        ws = _rs_ws[device] = torch.empty(lib().b200_reduce_scatter_pull_workspace_floats(), dtype=torch.float32, device=device)
+    arr = (C.c_void_p * len(src_ptrs))(*src_ptrs)
+    check(lib().b200_reduce_scatter_pull_bf16(dst_ptr, arr, len(src_ptrs), int(n), _p(norm_sq), int(accumulate_norm), ws.data_ptr(), int(ctas),
+                                              stream if stream is not None else _st()), "b200_reduce_scatter_pull_bf16")
+    _count(2 if norm_sq is not None else 1)

@@ -102,6 +102,22 @@ int b200_adamw_step(void* p, const void* g, void* m, void* v, float* master, int
 /* dst += src (bf16), gradient accumulation helper */
 int b200_add_inplace_bf16(void* dst, const void* src, int64_t n, b200_stream_t stream);
 
+/* ---- NVLink peer-memory data path (replaces FSDP2's NCCL reduce_scatter / all_gather,
+ * torch/distributed/fsdp/_fully_shard/_fsdp_collectives.py:237-291,448-664 as set up by components/distributed/parallelizer.py:858-872).
+ * Buffers peers touch are allocated here (cudaMalloc) and exported/imported with CUDA IPC (64-byte handles). */
+int b200_mem_alloc(void** ptr, size_t bytes);
+int b200_mem_free(void* ptr);
+int b200_ipc_export(void* ptr, void* handle64);
+int b200_ipc_import(const void* handle64, void** ptr);
+int b200_ipc_close(void* ptr);
+/* copy-engine copy (peer-to-peer over NVLink when dst/src live on different GPUs): the all-gather push, zero SMs */
+int b200_copy_async(void* dst, const void* src, size_t bytes, b200_stream_t stream);
+/* reduce-scatter pull: dst[i] = bf16(sum_j srcs[j][i]) with fp32 accumulation in source order (srcs[0] = own slice, may alias dst;
+ * srcs[1..] = peer-mapped views of the same slice); norm_sq[0] (=|+=) sum of squares of the result (grad-norm fused in). */
+int b200_reduce_scatter_pull_workspace_floats(void);
+int b200_reduce_scatter_pull_bf16(void* dst, const void* const* srcs, int nsrc, int64_t n, float* norm_sq, int accumulate_norm,
+                                  float* workspace, int ctas, b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

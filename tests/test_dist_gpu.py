@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 from tests.golden_utils import load, model_cfg, init_params, batches  # noqa: E402
 
 
-def _worker(rank, world, port, out_q):
+def _worker(rank, world, port, out_q, peer_comm="1"):
+    os.environ["B200_PEER_COMM"] = peer_comm
     import torch.distributed as dist
     from automodel_b200.engine import ShardedLlamaEngine
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
@@ -39,11 +40,12 @@ def _worker(rank, world, port, out_q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_world2_nccl_matches_reference_curve():
+@pytest.mark.parametrize("peer_comm", ["1", "0"], ids=["nvlink_peer_path", "nccl_collectives"])
+def test_world2_matches_reference_curve(peer_comm):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 1000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29700 + (os.getpid() % 1000) + (7 if peer_comm == "0" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, peer_comm)) for r in range(2)]
     for p in procs:
         p.start()
     res, same = q.get(timeout=600)

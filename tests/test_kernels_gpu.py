@@ -340,3 +340,25 @@ def test_adamw_matches_oracle(mode):
             # fp32 oracle keeps fp32 params; ours stores bf16: compare against rounding of the oracle trajectory
             assert np.abs(got - params["w"]).max() <= 2.0 ** -8 * np.abs(params["w"]).max() * step + 1e-6
             params["w"] = got.copy(); opt.m["w"] = m.float().cpu().numpy(); opt.v["w"] = v.float().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------ reduce-scatter pull kernel
+def test_reduce_scatter_pull_kernel_local_sources():
+    """The NVLink pull kernel on local buffers: fp32 accumulation in source order, in-place on source 0, fused sum of squares."""
+    n = 8 * 100_003
+    g = torch.Generator(device=DEV).manual_seed(9)
+    srcs = [bf(torch.randn(n, device=DEV, generator=g)) for _ in range(4)]
+    ref = bf(sum(s.float() for s in srcs[1:]) + srcs[0].float()) if False else None
+    acc = srcs[0].float()
+    for s in srcs[1:]:
+        acc = acc + s.float()
+    ref = bf(acc)
+    nsq = torch.full((1,), 123.0, device=DEV)
+    ops.reduce_scatter_pull_(srcs[0].data_ptr(), [s.data_ptr() for s in srcs], n, nsq, False, torch.device(DEV), ctas=16)
+    torch.cuda.synchronize()
+    assert torch.equal(srcs[0], ref)
+    expect = ref.double().pow(2).sum().item()
+    assert abs(nsq.item() - expect) < 1e-5 * expect
+    ops.reduce_scatter_pull_(srcs[1].data_ptr(), [srcs[1].data_ptr()], n, nsq, True, torch.device(DEV), ctas=7)
+    expect2 = expect + srcs[1].double().pow(2).sum().item()
+    assert abs(nsq.item() - expect2) < 1e-5 * expect2

@@ -3,9 +3,7 @@ run() { # name, env...
   name=$1; shift
   env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r1_n2_$name.json 2> gpurun_out/r1_n2_$name.err
   python -c "
-import json; d=json.load(open('gpurun_out/r1_n2_$name.json')); print('$name', d['n_gpus'], round(d['value']), round(d['ms_per_step'],1), round(d['roofline']['achieved']), d['clocks']['sm_mhz'])"
+import json; d=json.load(open('gpurun_out/r1_n2_$name.json')); print('$name', d['n_gpus'], round(d['value']), round(d['ms_per_step'],1), round(d['roofline']['achieved']), d['clocks']['sm_mhz'], d['final_loss'])" || tail -5 gpurun_out/r1_n2_$name.err
 }
-run sms0 B200_COMM_SMS=0 NCCL_MAX_CTAS=32
-run sms8 B200_COMM_SMS=8
-run sms16 B200_COMM_SMS=16
-run sms4 B200_COMM_SMS=4
+run peer B200_PEER_COMM=1
+run nccl B200_PEER_COMM=0
