@@ -59,6 +59,7 @@ int reduce_scatter_pull_bf16(void*, const void* const*, int, int64_t, float*, in
 // debug option: 1 (default) = tcgen05/TMEM attention, 0 = the mma.sync v1 kernels (kept for bisecting only)
 static int g_attn_impl = 1;
 extern int forced_bn;
+extern int use_pair;
 
 // ---------------------------------------------------------------- cuBLASLt comparator (bench / tests only)
 int gemm_bf16_cublaslt(int kind, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K, void* ws,
@@ -124,6 +125,7 @@ int b200_abi_version(void) { return 1; }
 int b200_set_option(const char* name, int value) {
   if (name && !strcmp(name, "attn_impl")) { g_attn_impl = value; return 0; }
   if (name && !strcmp(name, "gemm_bn")) { b200::forced_bn = value; return 0; }
+  if (name && !strcmp(name, "gemm_2cta")) { b200::use_pair = value; return 0; }
   return set_error(B200_ERR_ARG, "unknown option %s", name ? name : "(null)");
 }
 

@@ -383,11 +383,16 @@ static int gemm_dispatch_kind(int kind, const void* A, int lda, const void* B, i
 }
 
 int forced_bn = 0;  // debug: b200_set_option("gemm_bn", 128|192|256) pins the tile width
+int use_pair = 0;   // b200_set_option("gemm_2cta", 1): CTA-pair kernel (gemm_tcgen05_2cta.cu) for problems with M, N >= 256
+int gemm_bf16_tcgen05_pair(int kind, const void* A, int lda, const void* B, int ldb, void* C, int ldc, const void* R, int ldr, int M, int N,
+                           int K, int flags, int group_m, int max_ctas, cudaStream_t stream);
 
 int gemm_bf16_tcgen05(int kind, const void* A, int lda, const void* B, int ldb, void* C, int ldc, const void* R, int ldr,
                       int M, int N, int K, int flags, int group_m, int max_ctas, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(B200_ERR_ARG, "gemm: empty problem %dx%dx%d", M, N, K);
   if ((flags & GEMM_FLAG_RESIDUAL) && !R) return set_error(B200_ERR_ARG, "gemm: residual flag without R");
+  if (use_pair && M >= 256 && N >= 256 && forced_bn == 0)
+    return gemm_bf16_tcgen05_pair(kind, A, lda, B, ldb, C, ldc, R, ldr, M, N, K, flags, group_m, max_ctas, stream);
   if (group_m <= 0) group_m = 8;
   // 128x256 tiles whenever N allows (measured: 128x192 / 128x128 tiles lose more in per-tile efficiency than they win back in
   // wave quantisation on every Llama-3-8B shape, profiles/r1_gemm_tile_sweep.md)

@@ -230,13 +230,21 @@ def main():
     l0 = ops.LAUNCHES
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
+    h0 = time.perf_counter()
     for _ in range(args.steps):
         loss, gn = eng.train_step(None, 1.0, num_label_tokens=n_label, staged=staged)
+    host_issue_ms = (time.perf_counter() - h0) * 1e3 / args.steps   # CPU time to enqueue one step (back-pressured by the launch queue)
     t1.record()
     barrier()
     if args.profile:
         torch.cuda.profiler.stop()
     ops.GEMM_TIMER = None
+    # pure host cost of enqueueing one step: start from an idle GPU so the launch queue never back-pressures
+    torch.cuda.synchronize()
+    h0 = time.perf_counter()
+    eng.train_step(None, 1.0, num_label_tokens=n_label, staged=staged)
+    host_only_ms = (time.perf_counter() - h0) * 1e3
+    torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     launches = ops.LAUNCHES - l0
     ms = t0.elapsed_time(t1)
@@ -296,7 +304,7 @@ def main():
                        "clip_grad_norm": 1.0, "l2": "working set (16 GB params + 16 GB grads + activations) >> 126 MB L2; no flush needed",
                        "tokens_per_step": tokens_per_step},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "final_loss": final_loss,
-            "flops_per_token": f_tok}
+            "flops_per_token": f_tok, "host_issue_ms_per_step": host_issue_ms, "host_enqueue_ms_idle_gpu": host_only_ms}
     if args.profile:
         line["profile_mode"] = True
     if not args.no_cpu_baseline and not args.profile and world == 1:

@@ -7,7 +7,8 @@ CASE = r'''
 import sys, torch
 sys.path.insert(0, %r)
 from automodel_b200 import ops
-kind, M, N, K = %d, %d, %d, %d
+kind, M, N, K, pair = %d, %d, %d, %d, %d
+ops.set_option("gemm_2cta", pair)
 g = torch.Generator(device="cuda").manual_seed(1)
 mk = lambda s: torch.randint(-3, 4, s, device="cuda", generator=g).float().bfloat16()
 a = mk((M, K) if kind != 2 else (K, M)); b = mk((N, K) if kind == 0 else (K, N))
@@ -15,14 +16,16 @@ out = ops.gemm(kind, a, b); torch.cuda.synchronize()
 af, bfl = a.float(), b.float()
 ref = (af @ bfl.t() if kind == 0 else af @ bfl if kind == 1 else af.t() @ bfl).bfloat16()
 bad = (out != ref)
-print("RESULT kind=%%d %%dx%%dx%%d mismatches=%%d/%%d" %% (kind, M, N, K, int(bad.sum()), bad.numel()))
+print("RESULT pair=%%d kind=%%d %%dx%%dx%%d mismatches=%%d/%%d" %% (pair, kind, M, N, K, int(bad.sum()), bad.numel()))
 if bad.any():
     idx = bad.nonzero()[:8].tolist()
     print("  first bad:", [(i, j, out[i, j].item(), ref[i, j].item()) for i, j in idx])
     rows = bad.any(1).nonzero().flatten(); cols = bad.any(0).nonzero().flatten()
     print("  bad rows: n=%%d min=%%d max=%%d ; bad cols: n=%%d min=%%d max=%%d" %% (len(rows), rows.min(), rows.max(), len(cols), cols.min(), cols.max()))
 '''
-cases = [(k, *s) for k in (0, 1, 2) for s in [(128, 256, 64), (128, 192, 64), (256, 512, 128), (128, 128, 64), (384, 320, 192), (512, 960, 320), (4096, 6144, 4096)]]
+cases = [(k, *s, 1) for k in (0, 1, 2) for s in [(256, 256, 64), (256, 256, 256), (512, 512, 128), (384, 320, 192), (1000, 776, 328), (4096, 6144, 4096)]]
+if "--all" in sys.argv:
+    cases += [(k, *s, 0) for k in (0, 1, 2) for s in [(128, 256, 64), (256, 512, 128), (128, 128, 64), (384, 320, 192), (4096, 6144, 4096)]]
 fails = 0
 for c in cases:
     t0 = time.time()
@@ -49,7 +52,9 @@ if "--bench" in sys.argv and fails == 0:
             def f():
                 ops.set_option("gemm_bn", bn); ops.gemm(kind, a, b, out=out); ops.set_option("gemm_bn", 0)
             return f
-        for name, fn in [("tcgen05", lambda: ops.gemm(kind, a, b, out=out)), ("tc_bn256", mk(256)), ("tc_bn192", mk(192)), ("tc_bn128", mk(128)),
+        def pair():
+            ops.set_option("gemm_2cta", 1); ops.gemm(kind, a, b, out=out); ops.set_option("gemm_2cta", 0)
+        for name, fn in [("tcgen05_1cta", lambda: ops.gemm(kind, a, b, out=out)), ("tcgen05_2cta", pair),
                          ("cublasLt", lambda: ops.gemm_cublaslt(kind, a, b, out=out))]:
             for _ in range(3): fn()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
