@@ -383,7 +383,7 @@ static int gemm_dispatch_kind(int kind, const void* A, int lda, const void* B, i
 }
 
 int forced_bn = 0;  // debug: b200_set_option("gemm_bn", 128|192|256) pins the tile width
-int use_pair = 0;   // b200_set_option("gemm_2cta", 1): CTA-pair kernel (gemm_tcgen05_2cta.cu) for problems with M, N >= 256
+int use_pair = 1;   // b200_set_option("gemm_2cta", 0|1): CTA-pair kernel (gemm_tcgen05_2cta.cu) for problems with M, N >= 256
 int gemm_bf16_tcgen05_pair(int kind, const void* A, int lda, const void* B, int ldb, void* C, int ldc, const void* R, int ldr, int M, int N,
                            int K, int flags, int group_m, int max_ctas, cudaStream_t stream);
 

@@ -26,7 +26,8 @@ def assert_close_bf16(got, ref_fp32, ulps=2, atol=0.0, what=""):
 
 
 # ------------------------------------------------------------------------------------------------ GEMM
-GEMM_SHAPES = [(128, 256, 64), (256, 256, 256), (1024, 512, 256), (384, 320, 192), (200, 264, 72), (1024, 1024, 512), (4096, 1536, 1024)]
+GEMM_SHAPES = [(128, 256, 64), (256, 256, 256), (1024, 512, 256), (384, 320, 192), (200, 264, 72), (1000, 776, 328), (1024, 1024, 512),
+               (4096, 1536, 1024)]
 
 
 def _gemm_ref(kind, a, b):
@@ -44,9 +45,17 @@ def _gemm_inputs(kind, M, N, K, gen):
     return gen(a_shape), gen(b_shape)
 
 
+@pytest.fixture
+def gemm_2cta(request):
+    ops.set_option("gemm_2cta", request.param)
+    yield request.param
+    ops.set_option("gemm_2cta", 1)
+
+
+@pytest.mark.parametrize("gemm_2cta", [1, 0], indirect=True, ids=["cta_pair", "single_cta"])
 @pytest.mark.parametrize("kind", [ops.NT, ops.NN, ops.TN])
 @pytest.mark.parametrize("shape", GEMM_SHAPES)
-def test_gemm_exact_small_integers(kind, shape):
+def test_gemm_exact_small_integers(kind, shape, gemm_2cta):
     """Integer-valued operands: every partial sum is exact in fp32, so tcgen05 must reproduce the result BIT-exactly
     (any descriptor / swizzle / layout mistake shows up as a wrong integer)."""
     M, N, K = shape
