@@ -353,7 +353,7 @@ class ShardedLlamaEngine:
         if T > self.max_tokens:
             raise ValueError(f"micro-batch of {T} tokens exceeds max_tokens={self.max_tokens}")
         if position_ids is None:
-            pos_np = np.ascontiguousarray(np.broadcast_to(np.arange(S, dtype=np.int64), (b, S)))
+            pos_np = np.tile(np.arange(S, dtype=np.int64), (b, 1))
         else:
             pos_np = position_ids.cpu().numpy()
         cu_np, max_len = cu_seqlens_from_position_ids(pos_np)
@@ -385,19 +385,35 @@ class ShardedLlamaEngine:
         """One micro-batch.  Loss (already divided by the GLOBAL label-token count, train_ft.py:1449-1473) accumulates in
         self.loss_dev; parameter gradients (= or +=) land in the flat gradient buffers; on the last micro-batch each unit's
         gradients are reduce-scattered as soon as its backward is done."""
-        ops, d, A, tmp = self.ops, self.dims, self.act, self.tmp
+        handle = staged if staged is not None else self._stage_inputs(input_ids, labels, position_ids)
+        self.forward_logits(handle)
+        self.fused_loss(handle, num_label_tokens)
+        self.backward_from_dlogits(handle, first_micro=first_micro, last_micro=last_micro)
+
+    def _views(self, handle):
+        k, T, nseq, max_len = handle
+        devb = self._in_dev[k]
+        return T, nseq, max_len, devb[0:T], devb[T:2 * T], devb[2 * T:3 * T], devb[3 * T:3 * T + nseq + 1]
+
+    def fused_loss(self, handle, num_label_tokens):
+        """MaskedCrossEntropy fused with its backward (components/loss/masked_ce.py:73-89): the loss accumulates on the device,
+        the logits buffer becomes dlogits in place."""
+        T, _, _, _, lab, _, _ = self._views(handle)
+        self.ops.ce_fwd_bwd_(self.logits[:T], lab, num_label_tokens, self.loss_dev, accumulate=True, row_loss=self.row_loss[:T])
+
+    def forward_logits(self, handle):
+        """Forward of one staged micro-batch up to the bf16 logits [T, V] (a view of the engine's logits buffer); every activation the
+        backward needs stays in the arenas."""
+        ops, d, A = self.ops, self.dims, self.act
         ctas = self.gemm_ctas
 
         def G(*a, **k):
             return ops.gemm(*a, max_ctas=ctas, **k)
 
-        k, T, nseq, max_len = staged if staged is not None else self._stage_inputs(input_ids, labels, position_ids)
-        devb = self._in_dev[k]
-        ids, lab, pos, cu = devb[0:T], devb[T:2 * T], devb[2 * T:3 * T], devb[3 * T:3 * T + nseq + 1]
+        T, nseq, max_len, ids, lab, pos, cu = self._views(handle)
         L, Hq, Hkv, D = d.layers, d.heads, d.kv_heads, d.head_dim
         qc, kc = d.q_cols, d.kv_cols
         rba = self.round_before_add
-        acc = not first_micro
         sl = lambda t: t[:T]
 
         # ---------------- forward (models/llama/model.py:293-388, 203-234)
@@ -424,10 +440,22 @@ class ShardedLlamaEngine:
         ops.rmsnorm_fwd(hL, self.P["model.norm.weight"], d.eps, out=xf, rstd=sl(self.rstdf))
         logits = sl(self.logits)
         G(ops.NT, xf, self.P["lm_head.weight"], out=logits)
-        # fused CE: loss accumulates on the device, logits become dlogits in place (components/loss/masked_ce.py:73-89)
-        ops.ce_fwd_bwd_(logits, lab, num_label_tokens, self.loss_dev, accumulate=True, row_loss=sl(self.row_loss))
+        return logits
 
-        # ---------------- backward
+    def backward_from_dlogits(self, handle, first_micro=True, last_micro=True):
+        """Backward of one staged micro-batch; self.logits[:T] must hold d(loss)/d(logits) in bf16."""
+        ops, d, A, tmp = self.ops, self.dims, self.act, self.tmp
+        ctas = self.gemm_ctas
+
+        def G(*a, **k):
+            return ops.gemm(*a, max_ctas=ctas, **k)
+
+        T, nseq, max_len, ids, lab, pos, cu = self._views(handle)
+        L, Hq, Hkv, D = d.layers, d.heads, d.kv_heads, d.head_dim
+        qc, kc = d.q_cols, d.kv_cols
+        acc = not first_micro
+        sl = lambda t: t[:T]
+        hL, xf, logits = sl(A["h"][L]), sl(self.xf), sl(self.logits)
         head_ui = 1 + L
         G(ops.TN, logits, xf, out=self.G["lm_head.weight"], residual=self.G["lm_head.weight"] if acc else None)
         dxf = sl(tmp["dxf"])
@@ -474,10 +502,12 @@ class ShardedLlamaEngine:
     def optimizer_step(self, max_grad_norm: Optional[float] = 1.0, lr: Optional[float] = None):
         """components/training/utils.py:65-171 + train_ft.py:1556-1558 on the flat shards.  Returns the device scalar
         holding the squared global grad norm (sqrt on the host only for logging)."""
+        self.compute_grad_norm_sq()
+        return self.apply_adamw(max_grad_norm, lr)
+
+    def compute_grad_norm_sq(self):
+        """Global squared gradient norm over the (reduce-scattered) shards -> self.norm_sq (device scalar)."""
         ops = self.ops
-        if lr is not None:
-            self.lr = lr
-        self.step_count += 1
         nu = len(self.units)
         fused_norm = self.peer is not None and getattr(self, "_rs_started", False)
         for ui in range(nu):
@@ -491,7 +521,15 @@ class ShardedLlamaEngine:
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.norm_sq, op=dist.ReduceOp.SUM, group=self.pg)
-        for ui in range(nu):
+        return self.norm_sq
+
+    def apply_adamw(self, max_grad_norm: Optional[float] = 1.0, lr: Optional[float] = None):
+        """Fused AdamW (+ clip by the norm in self.norm_sq) on every unit shard, then the in-place parameter all-gather."""
+        ops = self.ops
+        if lr is not None:
+            self.lr = lr
+        self.step_count += 1
+        for ui in range(len(self.units)):
             ops.adamw_step_(self.shard(self.p_full, ui), self.shard(self.g_full, ui), self.m[ui], self.v[ui], self.lr, self.betas[0],
                             self.betas[1], self.eps, self.wd, self.step_count, max_grad_norm=max_grad_norm or 0.0,
                             grad_norm_sq=self.norm_sq, mode=self.adam_mode, master=None if self.master is None else self.master[ui])

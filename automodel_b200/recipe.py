@@ -1,0 +1,220 @@
+"""Reference-facing surface of the B200 sharded step: what the `automodel` recipe (unchanged) binds to.
+
+Mirrors the reference's extension points for this path:
+
+  * `B200ShardedConfig` / `B200ShardedManager.parallelize(model)`  <->  FSDP2Config / FSDP2Manager.parallelize
+        (components/distributed/config.py:49-136, fsdp2.py:105-142; registered under distributed.strategy: b200_sharded)
+  * `B200CausalLM` (nn.Module)  <->  the FSDP-wrapped LlamaForCausalLM the recipe calls as `model(**batch).logits`
+        (recipes/llm/train_ft.py:1443-1457), with HF-named parameters / .grad views, `set_requires_gradient_sync`
+        (components/distributed/utils.py:222-247) and the grad-norm hook the clip utility needs for sharded flat grads
+        (components/training/utils.py:290-359)
+  * `B200MaskedCrossEntropy`  <->  loss_fn `_target_` called as `loss_fn(logits=, labels=, num_label_tokens=)`
+        (components/loss/utils.py:84-104, masked_ce.py:41-90) - fused with the engine's CE kernel
+  * `B200FusedAdamW`  <->  optimizer `_target_` called as `target(params=trainable_params, **yaml)` (train_ft.py:368); `.step()`,
+        `.zero_grad()`, mutable `.param_groups[0]["lr" | "weight_decay"]` for OptimizerParamScheduler (optim/scheduler.py:257-261)
+
+Host glue only: every device operation goes through ShardedLlamaEngine -> the C ABI.
+"""
+from dataclasses import dataclass
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .engine import ShardedLlamaEngine, IGNORE_INDEX
+
+
+@dataclass
+class B200ShardedConfig:
+    """YAML `distributed:` section for `strategy: b200_sharded` (same role as FSDP2Config)."""
+    max_tokens: int = 4096
+    adam_mode: int = 1               # 1: torch.optim.AdamW bf16 op sequence (reference default optimizer); 0: fp32 math
+    master_weights: bool = False
+    reference_rounding: bool = True  # bf16(bf16(acc) + residual), as the reference's two eager ops
+    max_positions: Optional[int] = None
+
+
+class _Fwd(torch.autograd.Function):
+    """The whole decoder stack as ONE autograd node: forward runs the engine up to the logits, backward consumes dlogits and runs the
+    engine backward (wgrads straight into the flat gradient buffers, reduce-scatter per unit).  Parameter gradients therefore do
+    not flow through autograd: they appear on the nn.Parameters as views of the flat buffers."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, handle, b, S):
+        eng = model.engine
+        logits = eng.forward_logits(handle)
+        ctx.model, ctx.handle = model, handle
+        return logits.view(b, S, -1)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        model, eng = ctx.model, ctx.model.engine
+        T = ctx.handle[1]
+        buf = eng.logits[:T]
+        d2 = dlogits.reshape(T, -1)
+        # the recipe back-propagates local_loss * dp_group_size (train_ft.py:1473) because FSDP2 averages; our reduce-scatter sums
+        scale = 1.0 / max(eng.world, 1)
+        if d2.data_ptr() != buf.data_ptr():
+            buf.copy_(d2 if scale == 1.0 else d2 * scale)
+        elif scale != 1.0:
+            buf.mul_(scale)
+        eng.backward_from_dlogits(ctx.handle, first_micro=model._first_micro, last_micro=model._sync_grads)
+        model._first_micro = False
+        return None, None, None, None, None
+
+
+class _FusedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, model, num_label_tokens):
+        eng = model.engine
+        before = eng.loss_dev.clone()
+        eng.fused_loss(model._last_handle, num_label_tokens)   # logits buffer now holds dlogits for a unit upstream gradient
+        ctx.model = model
+        return (eng.loss_dev - before)[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        # dlogits are already in the engine buffer (scaled by 1/num_label_tokens); fold the upstream scalar in
+        eng = ctx.model.engine
+        T = ctx.model._last_handle[1]
+        gv = float(g) if g.numel() == 1 else None
+        out = eng.logits[:T].view(ctx.model._last_shape[0], ctx.model._last_shape[1], -1)
+        if gv is not None and gv != 1.0:
+            out = out * gv
+        return out, None, None
+
+
+class B200CausalLM(nn.Module):
+    """nn.Module facade over ShardedLlamaEngine with the surface the recipe uses."""
+
+    def __init__(self, config, engine: ShardedLlamaEngine):
+        super().__init__()
+        self.config = config
+        self.engine = engine
+        self._sync_grads = True
+        self._first_micro = True
+        self._last_handle = None
+        self._last_shape = None
+        self._anchor = nn.Parameter(torch.zeros((), device=engine.device), requires_grad=True)  # keeps the autograd node alive
+        # HF-named parameters as views of the flat buffers; .grad = views of the flat gradient buffers
+        self._hf = {}
+        for name, p in engine.state_dict().items():
+            param = nn.Parameter(p, requires_grad=True)
+            param.grad = engine.named_grads()[name]
+            param._b200_engine = engine
+            self._hf[name] = param
+            self.register_parameter(name.replace(".", "__"), param)
+
+    # ---- reference surface
+    def named_parameters(self, prefix="", recurse=True, remove_duplicate=True):
+        for name, p in self._hf.items():
+            yield (prefix + ("." if prefix else "") + name, p)
+
+    def parameters(self, recurse=True):
+        for _, p in self.named_parameters():
+            yield p
+
+    def state_dict(self, *a, **k):
+        return {k_: v.detach() for k_, v in self.engine.state_dict().items()}
+
+    def set_requires_gradient_sync(self, flag: bool, recurse: bool = True):
+        """FSDPModule API used by get_sync_ctx: False on all but the last micro-batch (defer_fsdp_grad_sync)."""
+        self._sync_grads = bool(flag)
+
+    def forward(self, input_ids, position_ids=None, labels=None, attention_mask=None, **_ignored):
+        eng = self.engine
+        if labels is None:
+            labels = torch.full_like(input_ids, IGNORE_INDEX)
+        handle = eng.stage(input_ids.cpu() if input_ids.device.type != "cpu" else input_ids,
+                           labels.cpu() if labels.device.type != "cpu" else labels,
+                           None if position_ids is None else (position_ids.cpu() if position_ids.device.type != "cpu" else position_ids))
+        self._last_handle, self._last_shape = handle, tuple(input_ids.shape)
+        logits = _Fwd.apply(self._anchor, self, handle, input_ids.shape[0], input_ids.shape[1])
+        logits._b200_model = self
+        return SimpleNamespace(logits=logits)
+
+    # ---- hooks for the clip utility / optimizer
+    def b200_clip_grad_norm(self, max_norm: Optional[float]):
+        """components/training/utils.py:290-359 equivalent for the flat sharded grads: returns the global grad norm (device scalar);
+        the clip itself is applied inside the fused AdamW with this max_norm."""
+        self._max_norm = max_norm
+        self._norm_ready = True
+        return self.engine.compute_grad_norm_sq().sqrt()[0]
+
+    def b200_optimizer_step(self, lr=None):
+        if not getattr(self, "_norm_ready", False):
+            self.engine.compute_grad_norm_sq()
+        self.engine.apply_adamw(getattr(self, "_max_norm", None), lr=lr)
+        self._norm_ready = False
+        self._first_micro = True
+
+
+class B200MaskedCrossEntropy(nn.Module):
+    """Drop-in for components/loss/masked_ce.py:MaskedCrossEntropy when the model is a B200CausalLM: same call signature and
+    value (sum of token NLL / num_label_tokens, ignore_index -100, exactly 0 when there are no label tokens), computed by the
+    fused CE kernel on the engine's logits buffer."""
+
+    def __init__(self, fp32_upcast: bool = True, ignore_index: int = IGNORE_INDEX, reduction: str = "sum"):
+        super().__init__()
+        assert ignore_index == IGNORE_INDEX and reduction == "sum"
+
+    def forward(self, logits, labels, mask=None, num_label_tokens: Optional[int] = None):
+        model = getattr(logits, "_b200_model", None)
+        if model is None:
+            raise TypeError("B200MaskedCrossEntropy needs the logits of a B200CausalLM forward (no torch fallback on this path)")
+        if mask is not None:
+            raise NotImplementedError("mask= is not supported; pre-mask the labels with -100 (what the reference does internally)")
+        if num_label_tokens is None:
+            num_label_tokens = int((labels != IGNORE_INDEX).sum())
+        return _FusedLoss.apply(logits, model, int(num_label_tokens))
+
+
+class B200FusedAdamW(torch.optim.Optimizer):
+    """optimizer `_target_`: fused AdamW on the flat shards of the engine that owns `params`."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1):
+        params = list(params)
+        engines = {id(getattr(p, "_b200_engine", None)): getattr(p, "_b200_engine", None) for p in params}
+        if len(engines) != 1 or None in engines.values():
+            raise TypeError("B200FusedAdamW needs the parameters of ONE B200CausalLM")
+        self.engine = next(iter(engines.values()))
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._model = None
+
+    def attach(self, model: B200CausalLM):
+        self._model = model
+        return self
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        g = self.param_groups[0]
+        e = self.engine
+        e.betas, e.eps, e.wd = tuple(g["betas"]), g["eps"], g["weight_decay"]
+        if self._model is not None:
+            self._model.b200_optimizer_step(lr=g["lr"])
+        else:
+            e.optimizer_step(None, lr=g["lr"])
+
+    def zero_grad(self, set_to_none: bool = True):
+        return None  # wgrad epilogues overwrite the flat buffers on the first micro-batch of the next step
+
+
+class B200ShardedManager:
+    """`.parallelize(model)` of the new distributed strategy."""
+
+    def __init__(self, config: B200ShardedConfig, process_group=None, device=None, ops=None):
+        self.config, self.pg, self.device, self.ops = config, process_group, device, ops
+
+    def parallelize(self, model, optimizer_defaults=None):
+        cfg = model.config if hasattr(model, "config") else model
+        dev = self.device if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+        od = optimizer_defaults or {}
+        eng = ShardedLlamaEngine(cfg.to_dict() if hasattr(cfg, "to_dict") else cfg, dev, process_group=self.pg, max_tokens=self.config.max_tokens,
+                                 adam_mode=self.config.adam_mode, master_weights=self.config.master_weights,
+                                 reference_rounding=self.config.reference_rounding, max_positions=self.config.max_positions, ops=self.ops, **od)
+        if hasattr(model, "state_dict") and any(True for _ in model.state_dict()):
+            sd = {k: v for k, v in model.state_dict().items()}
+            if all(getattr(v, "device", torch.device("cpu")).type != "meta" for v in sd.values()):
+                eng.load_state_dict(sd)
+        return B200CausalLM(cfg, eng)
