@@ -34,13 +34,14 @@ struct AttnFwdSmem {
   static constexpr int K_OFF = TILE;
   static constexpr int V_OFF = 3 * TILE;
   static constexpr int P_OFF = 5 * TILE;
-  static constexpr int BAR_OFF = P_OFF + P_BYTES;
+  static constexpr int XCH_OFF = P_OFF + P_BYTES;        // float [2][2][128] running-max exchange + [2][128] row-sum exchange
+  static constexpr int BAR_OFF = XCH_OFF + 768 * 4;
   static constexpr int NUM_BARS = 1 + 4 + 4 + 2 + 2 + 1 + 1;  // q_full, k_full/empty[2], v_full/empty[2], s_full[2], s_free[2], p_ready, pv_done
   static constexpr int DYN = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
 };
 
 template <int D>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ o, float* __restrict__ lse,
                    const int* __restrict__ cu_seqlens, int64_t ldo, int Hq, int Hkv, int T, float scale_log2) {
@@ -81,9 +82,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 4);
+      mbar_init(&s_free[i], 8);
     }
-    mbar_init(p_ready, 4);
+    mbar_init(p_ready, 8);
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
@@ -160,20 +161,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else {
-    // ===================================================== softmax warps (one q row per thread)
+    // ===================================================== 8 softmax warps: thread <-> (q row r, half of the 128 kv columns).
+    // Two warps per scheduler (instead of one) hide TMEM / MUFU latency; the two halves of a row agree on the running max through
+    // shared memory (one named barrier per kv tile) and keep separate row sums that are combined once at the end.
     const int quad = warp & 3;                   // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;            // 0: kv columns [0,64), 1: [64,128)
     const int r = quad * 32 + lane;              // q row within the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const int qrow = m0 + r;                     // sequence-relative
     float m_used = 0.f, l_sum = 0.f;
-    uint8_t* p_row = smem + L::P_OFF + r * 128;
+    float* xch = reinterpret_cast<float*>(smem + L::XCH_OFF);  // [2 parity][2 halves][128 rows]
+    uint8_t* p_row = smem + L::P_OFF + half * 16384 + r * 128;  // this half's K-major atom of P
+    constexpr int OC = D / 64;                   // 32-column chunks of O owned by this half
     for (int j = 0; j < n_kv; ++j) {
       const int st = j & 1;
       mbar_wait(&s_full[st], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t v[4][32];
+      uint32_t v[2][32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tS0 + lane_addr + st * 128 + c * 32, v[c]);
+      for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tS0 + lane_addr + st * 128 + half * 64 + c * 32, v[c]);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -182,35 +188,41 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const bool need_mask = (j == mt) || ((j + 1) * 128 > len);
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           float x = __uint_as_float(v[c][e]) * scale_log2;
           if (need_mask) {
-            const int kv = j * 128 + c * 32 + e;
+            const int kv = j * 128 + half * 64 + c * 32 + e;
             if (kv > qrow || kv >= len) x = -INFINITY;
           }
           v[c][e] = __float_as_uint(x);
           mx = fmaxf(mx, x);
         }
       }
+      // row max over both halves
+      float* xc = xch + (j & 1) * 256;
+      xc[half * 128 + r] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, xc[(half ^ 1) * 128 + r]);
       if (j == 0) {
         m_used = (mx == -INFINITY) ? 0.f : mx;
       } else {
-        // lazy rescale: only when the running max grew by more than 8 (P stays <= 2^8, exact in the final O / l)
+        // lazy rescale: only when the running max grew by more than 8 (P stays <= 2^8, exact in the final O / l).
+        // Both halves of a row take the same decision (same mx, same m_used); each rescales its own half of the O columns.
         const bool grow = mx > m_used + 8.f;
         if (__any_sync(0xffffffffu, grow)) {
           mbar_wait(pv_done, (j - 1) & 1);  // O is quiescent: PV_{j-1} done, PV_j not yet issued
           tc_fence_after();
           const float f = grow ? ex2_approx(m_used - mx) : 1.f;
 #pragma unroll
-          for (int c = 0; c < D / 32; ++c) {
+          for (int c = 0; c < OC; ++c) {
             uint32_t ov[32];
-            tmem_ld_32x32b_x32(tO + lane_addr + c * 32, ov);
+            tmem_ld_32x32b_x32(tO + lane_addr + (half * OC + c) * 32, ov);
             tmem_ld_wait();
 #pragma unroll
             for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * f);
-            tmem_st_32x32b_x32(tO + lane_addr + c * 32, ov);
+            tmem_st_32x32b_x32(tO + lane_addr + (half * OC + c) * 32, ov);
           }
           tmem_st_wait();
           tc_fence_before();
@@ -218,11 +230,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           if (grow) m_used = mx;
         }
       }
-      // P = 2^(x - m), row sum, bf16 pack
-      uint32_t pk[64];
+      // P = 2^(x - m), partial row sum, bf16 pack
+      uint32_t pk[32];
       float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
           const float p0 = ex2_approx(__uint_as_float(v[c][e]) - m_used);
@@ -234,25 +246,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       l_sum += sum;
       if (j > 0) mbar_wait(pv_done, (j - 1) & 1);  // P buffer free (PV_{j-1} has read it)
 #pragma unroll
-      for (int ch = 0; ch < 16; ++ch) {  // 16 chunks of 8 kv columns; atom = ch / 8
+      for (int ch = 0; ch < 8; ++ch) {  // 8 chunks of 8 kv columns inside this half's atom
         uint4 val = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
-        *reinterpret_cast<uint4*>(p_row + (ch >> 3) * 16384 + (((ch & 7) ^ (r & 7)) << 4)) = val;
+        *reinterpret_cast<uint4*>(p_row + ((ch ^ (r & 7)) << 4)) = val;
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
     }
-    // epilogue: O / l -> bf16 -> global (each thread one contiguous row of D elements)
+    // epilogue: combine the two half row sums, O / l -> bf16 -> global (each thread half a row of D elements)
+    float* xl = xch + 512;  // [2 halves][128]
+    xl[half * 128 + r] = l_sum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l_sum += xl[(half ^ 1) * 128 + r];
     mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
     const float inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
     const bool valid = qrow < len;
-    if (valid) lse[static_cast<int64_t>(h) * T + s0 + qrow] = (m_used + log2f(l_sum)) * 0.6931471805599453f;
-    __nv_bfloat16* orow = o + static_cast<int64_t>(s0 + qrow) * ldo + h * D;
+    if (valid && half == 0) lse[static_cast<int64_t>(h) * T + s0 + qrow] = (m_used + log2f(l_sum)) * 0.6931471805599453f;
+    __nv_bfloat16* orow = o + static_cast<int64_t>(s0 + qrow) * ldo + h * D + half * (D / 2);
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = 0; c < OC; ++c) {
       uint32_t ov[32];
-      tmem_ld_32x32b_x32(tO + lane_addr + c * 32, ov);
+      tmem_ld_32x32b_x32(tO + lane_addr + (half * OC + c) * 32, ov);
       tmem_ld_wait();
       if (valid) {
 #pragma unroll
@@ -299,7 +315,7 @@ static int attn_fwd_tc_launch(const void* q, const void* k, const void* v, void*
   if ((rc = make_tmap_2d_bf16(&tk, k, T, static_cast<uint64_t>(Hkv) * D, ldk, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tv, v, T, static_cast<uint64_t>(Hkv) * D, ldv, 64, 128))) return rc;
   dim3 grid((max_len + 127) / 128, Hq, nseq);
-  kern<<<grid, 192, L::DYN, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(o), lse, cu, ldo, Hq, Hkv, T, scale * 1.4426950408889634f);
+  kern<<<grid, 320, L::DYN, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(o), lse, cu, ldo, Hq, Hkv, T, scale * 1.4426950408889634f);
   B200_CHECK_LAUNCH("attn_fwd_tc");
   return 0;
 }

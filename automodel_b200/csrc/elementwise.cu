@@ -210,14 +210,25 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const __nv_bfloat16* _
   }
 }
 
-__global__ void rmsnorm_dw_finalize_kernel(const float* __restrict__ partial, int nparts, int cols,
-                                           __nv_bfloat16* __restrict__ dw, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += partial[static_cast<size_t>(p) * cols + c];
-  if (accumulate) s = bf16_round(s) + __bfloat162float(dw[c]);
-  dw[c] = __float2bfloat16_rn(s);
+// 256 threads = 32 columns x 8 partial groups: the (up to ~300) per-CTA partials of a column are summed 8-way in parallel
+// (fixed order -> deterministic), instead of one thread walking all of them.
+__global__ void __launch_bounds__(256) rmsnorm_dw_finalize_kernel(const float* __restrict__ partial, int nparts, int cols,
+                                                                 __nv_bfloat16* __restrict__ dw, int accumulate) {
+  __shared__ float s[8][33];
+  const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float acc = 0.f;
+  if (c < cols)
+    for (int p = g; p < nparts; p += 8) acc += partial[static_cast<size_t>(p) * cols + c];
+  s[g][cx] = acc;
+  __syncthreads();
+  if (g == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += s[k][cx];
+    if (accumulate) t = bf16_round(t) + __bfloat162float(dw[c]);
+    dw[c] = __float2bfloat16_rn(t);
+  }
 }
 
 template <int VPL, int WPR>
@@ -263,7 +274,7 @@ static int rmsnorm_bwd_launch(const void* dy, const void* x, const void* w, cons
                                 static_cast<const __nv_bfloat16*>(w), rstd, static_cast<const __nv_bfloat16*>(dres),
                                 static_cast<__nv_bfloat16*>(dx), ws, rows);
   B200_CHECK_LAUNCH("rmsnorm_bwd");
-  rmsnorm_dw_finalize_kernel<<<(cols + 255) / 256, 256, 0, st>>>(ws, grid, cols, static_cast<__nv_bfloat16*>(dw), accumulate);
+  rmsnorm_dw_finalize_kernel<<<(cols + 31) / 32, 256, 0, st>>>(ws, grid, cols, static_cast<__nv_bfloat16*>(dw), accumulate);
   B200_CHECK_LAUNCH("rmsnorm_dw_finalize");
   return 0;
 }
