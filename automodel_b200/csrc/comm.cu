@@ -87,15 +87,21 @@ __global__ void __launch_bounds__(512) reduce_slices_kernel(uint4* __restrict__ 
     for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[u][e] = 0.f;
-    for (int j = 0; j < nsrc; ++j) {
-      uint4 v[UNROLL];
+    // two sources per round: 2*UNROLL independent 16-byte NVLink loads in flight per thread before the first use
+    for (int j = 0; j < nsrc; j += 2) {
+      uint4 v0[UNROLL], v1[UNROLL];
+      const bool two = j + 1 < nsrc;
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         const int64_t i = i0 + u * stride;
-        v[u] = i < nvec ? ld_peer(src.p[j] + i) : make_uint4(0, 0, 0, 0);
+        v0[u] = i < nvec ? ld_peer(src.p[j] + i) : make_uint4(0, 0, 0, 0);
+        v1[u] = (two && i < nvec) ? ld_peer(src.p[j + 1] + i) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) acc8(acc[u], v[u]);
+      for (int u = 0; u < UNROLL; ++u) {
+        acc8(acc[u], v0[u]);
+        acc8(acc[u], v1[u]);   // zeros when the source count is odd: the sum order stays source order
+      }
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -144,7 +150,7 @@ int reduce_scatter_pull_bf16(void* dst, const void* const* srcs, int nsrc, int64
   if (n % 8) return set_error(B200_ERR_ARG, "reduce_scatter_pull: n %% 8 != 0");
   PeerPtrs p;
   for (int j = 0; j < 8; ++j) p.p[j] = static_cast<const uint4*>(j < nsrc ? srcs[j] : nullptr);
-  if (ctas <= 0) ctas = 32;
+  if (ctas <= 0) ctas = 64;
   if (ctas > 256) ctas = 256;
   reduce_slices_kernel<4><<<ctas, 512, 0, st>>>(static_cast<uint4*>(dst), p, nsrc, n / 8, ws);
   B200_CHECK_LAUNCH("reduce_slices");

@@ -130,7 +130,7 @@ class ShardedLlamaEngine:
         # ---- persistent flat storage
         self.peer = None
         import os as _os
-        if self.world > 1 and dev.type == "cuda" and _os.environ.get("B200_PEER_COMM", "1") != "0":
+        if self.world > 1 and dev.type == "cuda" and _os.environ.get("B200_PEER_COMM", "0") == "1":
             # NVLink peer-memory data path (csrc/comm.cu): parameters and gradients of all units live in two IPC-exported slabs
             from .peer import Slab, PeerTable
             offs, tot = [], 0
@@ -286,12 +286,19 @@ class ShardedLlamaEngine:
             a, b = self.units[ui].shard_range(self.rank, self.world)
             off = (self._unit_off[ui] + a) * 2
             tab = self.peer[0]
+            if not hasattr(self, "_push_streams"):
+                self._push_streams = [torch.cuda.Stream(self.device) for _ in range(self.world - 1)]
+            # one stream per peer: the N-1 pushes of a unit run concurrently on different copy engines / NVLink ports
+            for k in range(1, self.world):
+                j = (self.rank + k) % self.world
+                ps = self._push_streams[k - 1]
+                st.wait(ev, ps)
+                self.ops.copy_async(tab.base[j] + off, tab.base[self.rank] + off, (b - a) * 2, ps.cuda_stream)
+                pe = st.event()
+                st.record(pe, ps)
+                st.wait(pe, st.comm)
             with torch.cuda.stream(st.comm):
                 st.wait(ev, st.comm)
-                cs = st.comm.cuda_stream
-                for k in range(1, self.world):
-                    j = (self.rank + k) % self.world
-                    self.ops.copy_async(tab.base[j] + off, tab.base[self.rank] + off, (b - a) * 2, cs)
                 dist.all_reduce(self._flag, group=self.pg)
                 done = st.event()
                 st.record(done, st.comm)
@@ -323,7 +330,7 @@ class ShardedLlamaEngine:
                 st.wait(ev, st.comm)
                 dist.all_reduce(self._flag, group=self.pg)
                 srcs = [tab.base[self.rank] + off] + [tab.base[(self.rank + k) % self.world] + off for k in range(1, self.world)]
-                self.ops.reduce_scatter_pull_(srcs[0], srcs, b - a, self.norm_sq, self._rs_started, self.device, stream=st.comm.cuda_stream)
+                self.ops.reduce_scatter_pull_(srcs[0], srcs, b - a, self.norm_sq, self._rs_started, self.device, ctas=64, stream=st.comm.cuda_stream)
                 self._rs_started = True
                 done = st.event()
                 st.record(done, st.comm)
