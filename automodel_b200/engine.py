@@ -76,6 +76,7 @@ class _Streams:
     def __init__(self, device):
         self.cuda = device.type == "cuda"
         self.comm = torch.cuda.Stream(device) if self.cuda else None
+        self.opt = torch.cuda.Stream(device) if self.cuda else None
 
     def event(self):
         return torch.cuda.Event() if self.cuda else None
@@ -157,6 +158,8 @@ class ShardedLlamaEngine:
                 self.P[s.name] = self.p_full[ui][s.offset:s.offset + s.numel].view(s.shape)
                 self.G[s.name] = self.g_full[ui][s.offset:s.offset + s.numel].view(s.shape)
         self._mk_fused_views()
+        self.ev_opt = [None] * len(self.units)  # AdamW of unit done (optimizer side stream)
+        self.ev_opt_all = None
         self.ev_ag = [None] * len(self.units)   # all-gather of unit done
         self.ev_rs = [None] * len(self.units)   # reduce-scatter of unit done
 
@@ -263,6 +266,7 @@ class ShardedLlamaEngine:
         self.load_state_dict(self.P)
 
     def state_dict(self):
+        self.sync_params()
         return dict(self.P)
 
     def named_grads(self):
@@ -348,9 +352,18 @@ class ShardedLlamaEngine:
             self.shard(self.g_full, ui).copy_(out)
 
     def _wait_params(self, ui):
+        """Unit ui's parameters are current: its AdamW (side stream) and, with N > 1, its all-gather have completed."""
+        if self.ev_opt[ui] is not None:
+            self.streams.wait(self.ev_opt[ui])
+            self.ev_opt[ui] = None
         if self.ev_ag[ui] is not None:
             self.streams.wait(self.ev_ag[ui])
             self.ev_ag[ui] = None
+
+    def sync_params(self):
+        """Make the current stream wait for every pending parameter update (state_dict readers, checkpointing)."""
+        for ui in range(len(self.units)):
+            self._wait_params(ui)
 
     # ------------------------------------------------------------------ forward + backward of one micro-batch
     def _stage_inputs(self, input_ids, labels, position_ids):
@@ -463,6 +476,9 @@ class ShardedLlamaEngine:
         acc = not first_micro
         sl = lambda t: t[:T]
         hL, xf, logits = sl(A["h"][L]), sl(self.xf), sl(self.logits)
+        if self.ev_opt_all is not None:   # the previous optimizer sweep (side stream) has consumed the gradient buffers / norm
+            self.streams.wait(self.ev_opt_all)
+            self.ev_opt_all = None
         head_ui = 1 + L
         G(ops.TN, logits, xf, out=self.G["lm_head.weight"], residual=self.G["lm_head.weight"] if acc else None)
         dxf = sl(tmp["dxf"])
@@ -536,11 +552,31 @@ class ShardedLlamaEngine:
         if lr is not None:
             self.lr = lr
         self.step_count += 1
-        for ui in range(len(self.units)):
-            ops.adamw_step_(self.shard(self.p_full, ui), self.shard(self.g_full, ui), self.m[ui], self.v[ui], self.lr, self.betas[0],
-                            self.betas[1], self.eps, self.wd, self.step_count, max_grad_norm=max_grad_norm or 0.0,
-                            grad_norm_sq=self.norm_sq, mode=self.adam_mode, master=None if self.master is None else self.master[ui])
-            self._all_gather_unit(ui)
+        st = self.streams
+
+        def run():
+            for ui in range(len(self.units)):
+                ops.adamw_step_(self.shard(self.p_full, ui), self.shard(self.g_full, ui), self.m[ui], self.v[ui], self.lr, self.betas[0],
+                                self.betas[1], self.eps, self.wd, self.step_count, max_grad_norm=max_grad_norm or 0.0,
+                                grad_norm_sq=self.norm_sq, mode=self.adam_mode, master=None if self.master is None else self.master[ui])
+                if st.cuda:
+                    ev = st.event()
+                    st.record(ev)
+                    self.ev_opt[ui] = ev
+                self._all_gather_unit(ui)
+
+        if st.cuda:
+            # The HBM-bound optimizer sweep runs on its own stream, unit by unit in forward order: the next step's forward (tensor-bound)
+            # starts as soon as the first units are updated and overlaps the rest (per-unit events gate each layer).
+            ready = st.event()
+            st.record(ready)
+            with torch.cuda.stream(st.opt):
+                st.wait(ready, st.opt)
+                run()
+                self.ev_opt_all = st.event()
+                st.record(self.ev_opt_all, st.opt)
+        else:
+            run()
         self._grads_dirty = False
         return self.norm_sq
 
