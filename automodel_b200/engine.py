@@ -130,6 +130,7 @@ class ShardedLlamaEngine:
 
         # ---- persistent flat storage
         self.peer = None
+        self._rs_started = False
         import os as _os
         if self.world > 1 and dev.type == "cuda" and _os.environ.get("B200_PEER_COMM", "0") == "1":
             # NVLink peer-memory data path (csrc/comm.cu): parameters and gradients of all units live in two IPC-exported slabs
@@ -144,7 +145,6 @@ class ShardedLlamaEngine:
             self.g_full = [self._g_slab.tensor[o:o + u.padded] for o, u in zip(offs, self.units)]
             self.peer = (PeerTable(self._p_slab, process_group), PeerTable(self._g_slab, process_group))
             self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
-            self._rs_started = False
         else:
             self.p_full = [torch.zeros(u.padded, dtype=bf, device=dev) for u in self.units]   # unsharded params (shard lives inside)
             self.g_full = [torch.zeros(u.padded, dtype=bf, device=dev) for u in self.units]   # unsharded grads (RS in place)
@@ -319,6 +319,18 @@ class ShardedLlamaEngine:
 
     def _reduce_scatter_unit(self, ui):
         if self.world == 1:
+            st = self.streams
+            if st.cuda:
+                # N = 1: nothing to reduce; the unit's grad-norm partial is taken now on the side stream, under the rest of the backward
+                ev = st.event()
+                st.record(ev)
+                with torch.cuda.stream(st.opt):
+                    st.wait(ev, st.opt)
+                    self.ops.sumsq_(self.g_full[ui], self.norm_sq, accumulate=self._rs_started)
+                    self._rs_started = True
+                    done = st.event()
+                    st.record(done, st.opt)
+                    self.ev_rs[ui] = done
             return
         import torch.distributed as dist
         st = self.streams
@@ -343,6 +355,8 @@ class ShardedLlamaEngine:
             with torch.cuda.stream(st.comm):
                 st.wait(ev, st.comm)
                 dist.reduce_scatter_tensor(self.shard(self.g_full, ui), self.g_full[ui], op=dist.ReduceOp.SUM, group=self.pg)
+                self.ops.sumsq_(self.shard(self.g_full, ui), self.norm_sq, accumulate=self._rs_started)  # grad-norm partial, off the critical path
+                self._rs_started = True
                 done = st.event()
                 st.record(done, st.comm)
                 self.ev_rs[ui] = done
@@ -532,7 +546,7 @@ class ShardedLlamaEngine:
         """Global squared gradient norm over the (reduce-scattered) shards -> self.norm_sq (device scalar)."""
         ops = self.ops
         nu = len(self.units)
-        fused_norm = self.peer is not None and getattr(self, "_rs_started", False)
+        fused_norm = self._rs_started   # the per-unit partials were already accumulated as each unit's gradients completed
         for ui in range(nu):
             if self.ev_rs[ui] is not None:
                 self.streams.wait(self.ev_rs[ui])

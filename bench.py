@@ -291,9 +291,17 @@ def main():
 
     peaks = measured_peaks()
     f_tok = flops_per_token(cfg, SEQ)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")   # from one ncu capture of the same command (tools/summarize_ncu.py traffic)
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath))["traffic_bytes_per_launch"]
+        except Exception:
+            traffic = None
     achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": achieved_tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": (achieved_tf / peaks["tflops_sustained"]) if achieved_tf else None, "traffic": None,
+                "frac": (achieved_tf / peaks["tflops_sustained"]) if achieved_tf else None, "traffic": traffic,
+                "traffic_unit": "DRAM bytes per GEMM launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, average over the step's GEMM launches)",
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_timed": n_gemm, "gemm_share_of_step": gemm_ms / (ms_step * args.steps),
                 "algorithmic_flops_per_step": gemm_flops / args.steps,

@@ -47,5 +47,23 @@ def report(src, dst):
     print(open(dst).read()[:6000])
 
 
+def traffic(src, dst):
+    """ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:gemm  -> average DRAM bytes per launch."""
+    import json
+    lines = [l for l in open(src) if not l.startswith("==")]
+    per = collections.defaultdict(lambda: collections.defaultdict(float))
+    for row in csv.DictReader(lines):
+        v = float(row["Metric Value"].replace(",", "")); u = row["Metric Unit"]
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1, "us": 1e3, "ms": 1e6}.get(u, 1)
+        per[row["ID"]][row["Metric Name"]] = v * mult
+    n = len(per)
+    rd = sum(d["dram__bytes_read.sum"] for d in per.values()); wr = sum(d["dram__bytes_write.sum"] for d in per.values())
+    t = sum(d["gpu__time_duration.sum"] for d in per.values())
+    out = {"kernel": "gemm_pair_kernel", "launches": n, "dram_bytes_read_per_launch": rd / n, "dram_bytes_write_per_launch": wr / n,
+           "traffic_bytes_per_launch": (rd + wr) / n, "avg_duration_us_under_ncu": t / n / 1e3, "source": src}
+    json.dump(out, open(dst, "w"), indent=1)
+    print(out)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "report": report, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
