@@ -290,19 +290,14 @@ class ShardedLlamaEngine:
             a, b = self.units[ui].shard_range(self.rank, self.world)
             off = (self._unit_off[ui] + a) * 2
             tab = self.peer[0]
-            if not hasattr(self, "_push_streams"):
-                self._push_streams = [torch.cuda.Stream(self.device) for _ in range(self.world - 1)]
-            # one stream per peer: the N-1 pushes of a unit run concurrently on different copy engines / NVLink ports
-            for k in range(1, self.world):
-                j = (self.rank + k) % self.world
-                ps = self._push_streams[k - 1]
-                st.wait(ev, ps)
-                self.ops.copy_async(tab.base[j] + off, tab.base[self.rank] + off, (b - a) * 2, ps.cuda_stream)
-                pe = st.event()
-                st.record(pe, ps)
-                st.wait(pe, st.comm)
+            # NOTE: issuing the N-1 pushes on separate streams (to spread them over the copy engines) was measured faster at N=2 but hung
+            # at N=8 (profiles/r1_n8_comm_paths.md); until that is understood the pushes stay on the single communication stream.
             with torch.cuda.stream(st.comm):
                 st.wait(ev, st.comm)
+                cs = st.comm.cuda_stream
+                for k in range(1, self.world):
+                    j = (self.rank + k) % self.world
+                    self.ops.copy_async(tab.base[j] + off, tab.base[self.rank] + off, (b - a) * 2, cs)
                 dist.all_reduce(self._flag, group=self.pg)
                 done = st.event()
                 st.record(done, st.comm)

@@ -141,6 +141,10 @@ def _emit(saved_fd, line):
 
 
 def main():
+    # watchdog: a wedged collective must not hold a multi-GPU box until the driver's own limit (SIGALRM's default action terminates
+    # the process even while it is blocked inside a CUDA / NCCL call)
+    import signal
+    signal.alarm(int(os.environ.get("B200_BENCH_WATCHDOG_S", "900")))
     saved_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
