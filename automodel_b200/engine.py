@@ -574,7 +574,8 @@ class ShardedLlamaEngine:
                     self.ev_opt[ui] = ev
                 self._all_gather_unit(ui)
 
-        if st.cuda:
+        import os as _os2
+        if st.cuda and _os2.environ.get("B200_OPT_OVERLAP", "1") != "0":
             # The HBM-bound optimizer sweep runs on its own stream, unit by unit in forward order: the next step's forward (tensor-bound)
             # starts as soon as the first units are updated and overlaps the rest (per-unit events gate each layer).
             ready = st.event()
