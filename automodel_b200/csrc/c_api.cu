@@ -56,6 +56,10 @@ int copy_async(void*, const void*, size_t, cudaStream_t);
 int reduce_scatter_pull_workspace_floats();
 int reduce_scatter_pull_bf16(void*, const void* const*, int, int64_t, float*, int, float*, int, cudaStream_t);
 
+int attn_fwd_tc64(const void*, const void*, const void*, void*, float*, const int*, int, int, int64_t, int64_t, int64_t, int64_t, int, int,
+                  int, int, float, cudaStream_t);
+static int g_attn_fwd_variant = 0;  // b200_set_option("attn_fwd_variant", 1): 64-row kv tiles, two CTAs per SM (attention_fwd64.cu)
+
 // debug option: 1 (default) = tcgen05/TMEM attention, 0 = the mma.sync v1 kernels (kept for bisecting only)
 static int g_attn_impl = 1;
 extern int forced_bn;
@@ -124,6 +128,7 @@ const char* b200_last_error(void) { return g_err; }
 int b200_abi_version(void) { return 1; }
 int b200_set_option(const char* name, int value) {
   if (name && !strcmp(name, "attn_impl")) { g_attn_impl = value; return 0; }
+  if (name && !strcmp(name, "attn_fwd_variant")) { g_attn_fwd_variant = value; return 0; }
   if (name && !strcmp(name, "gemm_bn")) { b200::forced_bn = value; return 0; }
   if (name && !strcmp(name, "gemm_2cta")) { b200::use_pair = value; return 0; }
   return set_error(B200_ERR_ARG, "unknown option %s", name ? name : "(null)");
@@ -173,6 +178,8 @@ int b200_embed_bwd(const int* ids, const void* dh, void* dW, int* workspace, int
 int b200_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const int* cu_seqlens, int nseq, int max_seqlen,
                   int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int Hq, int Hkv, int head_dim, int total_tokens, float scale,
                   b200_stream_t stream) {
+  if (g_attn_impl == 1 && g_attn_fwd_variant == 1)
+    return attn_fwd_tc64(q, k, v, o, lse, cu_seqlens, nseq, max_seqlen, ldq, ldk, ldv, ldo, Hq, Hkv, head_dim, total_tokens, scale, S(stream));
   if (g_attn_impl == 1)
     return attn_fwd_tc(q, k, v, o, lse, cu_seqlens, nseq, max_seqlen, ldq, ldk, ldv, ldo, Hq, Hkv, head_dim, total_tokens, scale, S(stream));
   return attn_fwd(q, k, v, o, lse, cu_seqlens, nseq, max_seqlen, ldq, ldk, ldv, ldo, Hq, Hkv, head_dim, total_tokens, scale, S(stream));

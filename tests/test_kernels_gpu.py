@@ -238,12 +238,18 @@ def _attn_ref(q, k, v, cu, Hq, Hkv, D, dout=None):
 
 @pytest.fixture
 def attn_impl(request):
-    ops.set_option("attn_impl", request.param)
+    impl, variant = request.param
+    ops.set_option("attn_impl", impl)
+    ops.set_option("attn_fwd_variant", variant)
     yield request.param
     ops.set_option("attn_impl", 1)
+    ops.set_option("attn_fwd_variant", DEFAULT_FWD_VARIANT)
 
 
-@pytest.mark.parametrize("attn_impl", [1, 0], indirect=True, ids=["tcgen05", "mma_v1"])
+DEFAULT_FWD_VARIANT = 0
+
+
+@pytest.mark.parametrize("attn_impl", [(1, 0), (1, 1), (0, 0)], indirect=True, ids=["tcgen05", "tcgen05_fwd64", "mma_v1"])
 @pytest.mark.parametrize("D,Hq,Hkv", [(64, 4, 2), (128, 4, 1), (128, 2, 2)])
 @pytest.mark.parametrize("lens", [[512], [64], [1], [200, 57, 255], [130, 1, 64, 63, 65], [1024, 129, 127, 128, 300]])
 def test_attention_fwd_bwd(D, Hq, Hkv, lens, attn_impl):
