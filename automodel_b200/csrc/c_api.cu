@@ -58,7 +58,7 @@ int reduce_scatter_pull_bf16(void*, const void* const*, int, int64_t, float*, in
 
 int attn_fwd_tc64(const void*, const void*, const void*, void*, float*, const int*, int, int, int64_t, int64_t, int64_t, int64_t, int, int,
                   int, int, float, cudaStream_t);
-static int g_attn_fwd_variant = 0;  // b200_set_option("attn_fwd_variant", 1): 64-row kv tiles, two CTAs per SM (attention_fwd64.cu)
+static int g_attn_fwd_variant = 1;  // 1 (default): 64-row kv tiles, two CTAs per SM (attention_fwd64.cu, 622 vs 510 TFLOP/s); 0: attention_tc.cu forward
 
 // debug option: 1 (default) = tcgen05/TMEM attention, 0 = the mma.sync v1 kernels (kept for bisecting only)
 static int g_attn_impl = 1;

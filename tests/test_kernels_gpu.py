@@ -246,7 +246,7 @@ def attn_impl(request):
     ops.set_option("attn_fwd_variant", DEFAULT_FWD_VARIANT)
 
 
-DEFAULT_FWD_VARIANT = 0
+DEFAULT_FWD_VARIANT = 1
 
 
 @pytest.mark.parametrize("attn_impl", [(1, 0), (1, 1), (0, 0)], indirect=True, ids=["tcgen05", "tcgen05_fwd64", "mma_v1"])
