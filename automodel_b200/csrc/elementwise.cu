@@ -51,6 +51,12 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {  // read-once data:
   return r;
 }
 
+__device__ __forceinline__ float rcp_fast(float x) {  // MUFU reciprocal (<= 1 ulp fp32): invisible after the bf16 rounding of the result
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 static int grid_for(int64_t work_items, int per_block, int max_blocks_per_sm = 8) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -357,7 +363,7 @@ __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const __nv_bfloat16* __
     unpack8(ld_stream(row + c), g);
     unpack8(ld_stream(row + vpr + c), u);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = bf16_round(g[e] / (1.f + __expf(-g[e]))) * u[e];
+    for (int e = 0; e < 8; ++e) o[e] = bf16_round(g[e] * rcp_fast(1.f + __expf(-g[e]))) * u[e];
     reinterpret_cast<uint4*>(a + t * F)[c] = pack8(o);
   }
 }
@@ -377,7 +383,7 @@ __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const __nv_bfloat16* __
     unpack8(ld_stream(reinterpret_cast<const uint4*>(da + t * F) + c), d);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float sg = 1.f / (1.f + __expf(-g[e]));
+      const float sg = rcp_fast(1.f + __expf(-g[e]));
       du[e] = d[e] * bf16_round(g[e] * sg);
       dg[e] = bf16_round(d[e] * u[e]) * (sg * (1.f + g[e] * (1.f - sg)));
     }
