@@ -363,7 +363,13 @@ int gemm_bf16_tcgen05_pair(int kind, const void* A, int lda, const void* B, int 
   } else {
     tR = tC;
   }
-  if (group_m <= 0) group_m = 4;  // in units of 256-row tiles
+  if (group_m <= 0) {
+    // L2 rasterisation (in 256-row tiles), from the sweep in profiles/r1_gemm_groupm_sweep.md: wide outputs (more column tiles than
+    // row tiles: gate/up, lm_head, da) walk all row tiles of a column panel first (the B panel is shared by the whole wave); square or
+    // tall outputs walk column tiles first.
+    const int tiles_m = (M + 2 * BM - 1) / (2 * BM), tiles_n = (N + BN - 1) / BN;
+    group_m = tiles_n > tiles_m ? (tiles_m < 16 ? tiles_m : 16) : 1;
+  }
   if (kind == GEMM_NT) return launch<false, false>(tA, tB, tC, tR, M, N, K, flags, group_m, max_ctas, stream);
   if (kind == GEMM_NN) return launch<false, true>(tA, tB, tC, tR, M, N, K, flags, group_m, max_ctas, stream);
   if (kind == GEMM_TN) return launch<true, true>(tA, tB, tC, tR, M, N, K, flags, group_m, max_ctas, stream);
