@@ -42,11 +42,21 @@ class _Cfg:
 
 @pytest.mark.parametrize("loss_kind", ["reference_loss", "fused_loss"])
 def test_recipe_loop_over_facade_matches_reference_fixture(loss_kind):
+    _run_recipe_loop(loss_kind, torch.device("cpu"), cpu_kernels)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("loss_kind", ["reference_loss", "fused_loss"])
+def test_recipe_loop_over_facade_on_gpu(loss_kind):
+    """Same loop on the B200 through the real kernels (C ABI)."""
+    _run_recipe_loop(loss_kind, torch.device("cuda", 0), None)
+
+
+def _run_recipe_loop(loss_kind, device, ops):
     z, meta = load("hd128_fp32")          # 2 micro-batches per step: exercises set_requires_gradient_sync / accumulation
     cfg = model_cfg(meta)
     oc = meta["optimizer"]
-    mgr = B200ShardedManager(B200ShardedConfig(max_tokens=meta["config"]["lbs"] * meta["config"]["seq"], adam_mode=1), device=torch.device("cpu"),
-                             ops=cpu_kernels)
+    mgr = B200ShardedManager(B200ShardedConfig(max_tokens=meta["config"]["lbs"] * meta["config"]["seq"], adam_mode=1), device=device, ops=ops)
     model = mgr.parallelize(_Cfg(cfg))
     assert isinstance(model, B200CausalLM)
     model.engine.load_state_dict(init_params(meta))
@@ -65,10 +75,11 @@ def test_recipe_loop_over_facade_matches_reference_fixture(loss_kind):
         for i, b in enumerate(mbs):
             model.set_requires_gradient_sync(i == len(mbs) - 1)
             labels = torch.from_numpy(b["labels"])
-            out = model(input_ids=torch.from_numpy(b["input_ids"]))
             if loss_kind == "fused_loss":
                 out = model(input_ids=torch.from_numpy(b["input_ids"]), labels=labels)
-            loss = loss_fn(out.logits, labels, num_label_tokens=n)
+            else:
+                out = model(input_ids=torch.from_numpy(b["input_ids"]))
+            loss = loss_fn(out.logits, labels.to(out.logits.device), num_label_tokens=n)
             (loss * dp).backward()
             total += float(loss.detach())
         gn = float(model.b200_clip_grad_norm(meta["max_grad_norm"]))
