@@ -57,6 +57,11 @@ __device__ __forceinline__ float rcp_fast(float x) {  // MUFU reciprocal (<= 1 u
   return y;
 }
 
+// b200_set_option("side_blocks_per_sm", k): k > 0 caps the HBM-bound sweeps that run on side streams next to the GEMMs (AdamW, grad-norm
+// partial sums) at k CTAs of 256 threads per SM.  At full occupancy one of these grid-stride kernels owns every register / thread slot of
+// the SM for its whole duration, so a GEMM CTA (28.7K registers) launched meanwhile cannot become resident and the "overlap" serialises.
+int side_blocks_per_sm = 0;
+
 static int grid_for(int64_t work_items, int per_block, int max_blocks_per_sm = 8) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -636,7 +641,7 @@ int sumsq_workspace_floats() { return 148 * 8; }
 // out[0] (+)= sum(g^2) over n bf16 values.  ws: sumsq_workspace_floats() floats.
 int sumsq_bf16(const void* g, int64_t n, float* out, float* ws, int accumulate, cudaStream_t st) {
   if (reinterpret_cast<uintptr_t>(g) & 15) return set_error(B200_ERR_ARG, "sumsq: 16B alignment required");
-  int grid = grid_for(n / 8, 512, 4);
+  int grid = grid_for(n / 8, 512, side_blocks_per_sm > 0 ? (side_blocks_per_sm + 1) / 2 : 4);
   if (grid > sumsq_workspace_floats()) grid = sumsq_workspace_floats();
   sumsq_partial_kernel<<<grid, 512, 0, st>>>(static_cast<const __nv_bfloat16*>(g), n, ws);
   B200_CHECK_LAUNCH("sumsq_partial");
@@ -751,7 +756,7 @@ int adamw_step(void* p, const void* g, void* m, void* v, float* master, int64_t 
   a.w2 = static_cast<float>(1.0 - b2);
   a.step_size = static_cast<float>(dlr / (1.0 - pow(b1, step)));
   a.bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(b2, step)));
-  const int grid = grid_for(n / 8, 256, 8);
+  const int grid = grid_for(n / 8, 256, side_blocks_per_sm > 0 ? side_blocks_per_sm : 8);
   auto P = static_cast<__nv_bfloat16*>(p);
   auto G = static_cast<const __nv_bfloat16*>(g);
   auto Mm = static_cast<__nv_bfloat16*>(m);

@@ -77,6 +77,7 @@ class _Streams:
         self.cuda = device.type == "cuda"
         self.comm = torch.cuda.Stream(device) if self.cuda else None
         self.opt = torch.cuda.Stream(device) if self.cuda else None
+        self.wg = torch.cuda.Stream(device) if self.cuda else None    # weight-gradient GEMMs (see backward_from_dlogits)
 
     def event(self):
         return torch.cuda.Event() if self.cuda else None
@@ -126,6 +127,17 @@ class ShardedLlamaEngine:
         self.round_before_add = bool(reference_rounding)
         self.step_count = 0
         self.streams = _Streams(self.device)
+        import os as _os0
+        # Weight-gradient GEMMs on their own stream: they are off the dgrad dependency chain, so they fill the tensor pipes while the
+        # chain runs its HBM-bound kernels (SwiGLU', RMSNorm', RoPE', attention pre/post passes) and the tail waves of the dgrad GEMMs.
+        # Default: on for one GPU (measured +2.3..3.4 %); with N > 1 it is opt-in until it has been measured next to the NCCL kernels.
+        self._wg_on = self.streams.cuda and _os0.environ.get("B200_WGRAD_STREAM", "1" if self.world == 1 else "0") == "1"
+        self.opt_overlap = self.streams.cuda and _os0.environ.get("B200_OPT_OVERLAP", "1") != "0"   # optimizer sweep on its own stream
+        self._wg_pending = {}     # tmp buffer name -> event of the last side-stream GEMM that reads it (WAR guard for the next writer)
+        self._wg_last = None
+        if self.streams.cuda:
+            # side-stream HBM-bound sweeps (AdamW, grad-norm partials) leave register/thread room for a co-resident GEMM CTA
+            self.ops.set_option("side_blocks_per_sm", int(_os0.environ.get("B200_SIDE_BLOCKS", "0")))
         bf, dev = torch.bfloat16, self.device
 
         # ---- persistent flat storage
@@ -313,6 +325,7 @@ class ShardedLlamaEngine:
             dist.all_gather_into_tensor(self.p_full[ui], self.shard(self.p_full, ui).clone(), group=self.pg)
 
     def _reduce_scatter_unit(self, ui):
+        wg = self._wg_last if self._wg_on else None   # the unit's weight gradients written on the wgrad stream
         if self.world == 1:
             st = self.streams
             if st.cuda:
@@ -321,6 +334,7 @@ class ShardedLlamaEngine:
                 st.record(ev)
                 with torch.cuda.stream(st.opt):
                     st.wait(ev, st.opt)
+                    st.wait(wg, st.opt)
                     self.ops.sumsq_(self.g_full[ui], self.norm_sq, accumulate=self._rs_started)
                     self._rs_started = True
                     done = st.event()
@@ -339,6 +353,7 @@ class ShardedLlamaEngine:
             tab = self.peer[1]
             with torch.cuda.stream(st.comm):
                 st.wait(ev, st.comm)
+                st.wait(wg, st.comm)
                 dist.all_reduce(self._flag, group=self.pg)
                 srcs = [tab.base[self.rank] + off] + [tab.base[(self.rank + k) % self.world] + off for k in range(1, self.world)]
                 self.ops.reduce_scatter_pull_(srcs[0], srcs, b - a, self.norm_sq, self._rs_started, self.device, ctas=64, stream=st.comm.cuda_stream)
@@ -349,6 +364,7 @@ class ShardedLlamaEngine:
         elif st.cuda:
             with torch.cuda.stream(st.comm):
                 st.wait(ev, st.comm)
+                st.wait(wg, st.comm)
                 dist.reduce_scatter_tensor(self.shard(self.g_full, ui), self.g_full[ui], op=dist.ReduceOp.SUM, group=self.pg)
                 self.ops.sumsq_(self.shard(self.g_full, ui), self.norm_sq, accumulate=self._rs_started)  # grad-norm partial, off the critical path
                 self._rs_started = True
@@ -368,6 +384,28 @@ class ShardedLlamaEngine:
         if self.ev_ag[ui] is not None:
             self.streams.wait(self.ev_ag[ui])
             self.ev_ag[ui] = None
+
+    def close(self):
+        """Drain the side streams.  The flat buffers are ordinary caching-allocator blocks owned by the allocating stream: if they were
+        released while an optimizer sweep, wgrad GEMM or collective of this engine is still in flight on another stream, the next
+        allocation could be handed memory those kernels are about to write."""
+        if self.streams.cuda:
+            torch.cuda.synchronize(self.device)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream_overlap(self, on: bool):
+        """Measurement aid: with overlap off every kernel of the step runs back to back on the compute stream (weight-gradient GEMMs and
+        the optimizer sweep included), so per-kernel CUDA-event durations are the kernels' own.  Results are identical either way."""
+        self.sync_params()
+        if self.streams.cuda:
+            torch.cuda.synchronize(self.device)
+        self._wg_on = bool(on) and self.streams.cuda
+        self.opt_overlap = bool(on) and self.streams.cuda
 
     def sync_params(self):
         """Make the current stream wait for every pending parameter update (state_dict readers, checkpointing)."""
@@ -479,20 +517,48 @@ class ShardedLlamaEngine:
         def G(*a, **k):
             return ops.gemm(*a, max_ctas=ctas, **k)
 
+        st = self.streams
+
+        def WG(reads, x, y, out):
+            """Weight-gradient GEMM out (+)= x^T y.  With the wgrad stream on it is issued there, behind an event that marks its inputs
+            complete on the compute stream; `reads` names the scratch buffers it reads so their next writer can wait for it."""
+            if not self._wg_on:
+                return G(ops.TN, x, y, out=out, residual=out if acc else None)
+            ev = st.event()
+            st.record(ev)
+            with torch.cuda.stream(st.wg):
+                st.wait(ev, st.wg)
+                G(ops.TN, x, y, out=out, residual=out if acc else None)
+                done = st.event()
+                st.record(done, st.wg)
+            for r in reads:
+                self._wg_pending[r] = done
+            self._wg_last = done
+
+        def before_write(name):
+            ev = self._wg_pending.pop(name, None)
+            if ev is not None:
+                st.wait(ev)
+
         T, nseq, max_len, ids, lab, pos, cu = self._views(handle)
         L, Hq, Hkv, D = d.layers, d.heads, d.kv_heads, d.head_dim
         qc, kc = d.q_cols, d.kv_cols
         acc = not first_micro
+        if first_micro:
+            self._rs_started = False   # a new accumulation window: grad-norm partials of an abandoned backward (no optimizer step) are dropped
         sl = lambda t: t[:T]
         hL, xf, logits = sl(A["h"][L]), sl(self.xf), sl(self.logits)
         if self.ev_opt_all is not None:   # the previous optimizer sweep (side stream) has consumed the gradient buffers / norm
-            self.streams.wait(self.ev_opt_all)
+            st.wait(self.ev_opt_all)
+            if self._wg_on:
+                st.wait(self.ev_opt_all, st.wg)
             self.ev_opt_all = None
         head_ui = 1 + L
-        G(ops.TN, logits, xf, out=self.G["lm_head.weight"], residual=self.G["lm_head.weight"] if acc else None)
+        WG((), logits, xf, self.G["lm_head.weight"])
         dxf = sl(tmp["dxf"])
         G(ops.NN, logits, self.P["lm_head.weight"], out=dxf)
         dh = sl(tmp["dh_a"]); dh_next = sl(tmp["dh_b"])
+        dh_name, dh_next_name = "dh_a", "dh_b"
         ops.rmsnorm_bwd(dxf, hL, self.P["model.norm.weight"], sl(self.rstdf), dx=dh, dw=self.G["model.norm.weight"],
                         accumulate_dw=acc, workspace=self.norm_ws)
         if last_micro:
@@ -503,24 +569,30 @@ class ShardedLlamaEngine:
             x2 = sl(A["x2"][l]); gu = sl(A["gu"][l]); a = sl(A["a"][l])
             da = sl(tmp["da"]); dgu = sl(tmp["dgu"]); dx = sl(tmp["dx"]); do2 = sl(tmp["do2"]); dqkv = sl(tmp["dqkv"])
             # MLP
-            G(ops.TN, dh, a, out=W["d_down"], residual=W["d_down"] if acc else None)
+            WG((dh_name,), dh, a, W["d_down"])
             G(ops.NN, dh, W["down"], out=da)
+            before_write("dgu")
             ops.swiglu_bwd(da, gu, out=dgu)
-            G(ops.TN, dgu, x2, out=W["d_gu"], residual=W["d_gu"] if acc else None)
+            WG(("dgu",), dgu, x2, W["d_gu"])
             G(ops.NN, dgu, W["gu"], out=dx)
             # dh1 = dh + rmsnorm'(dx2)
+            before_write(dh_next_name)
             ops.rmsnorm_bwd(dx, h1, W["n2"], sl(A["rstd2"][l]), dres=dh, dx=dh_next, dw=W["d_n2"], accumulate_dw=acc, workspace=self.norm_ws)
             dh, dh_next = dh_next, dh
+            dh_name, dh_next_name = dh_next_name, dh_name
             # attention
-            G(ops.TN, dh, o2, out=W["d_o"], residual=W["d_o"] if acc else None)
+            WG((dh_name,), dh, o2, W["d_o"])
             G(ops.NN, dh, W["o"], out=do2)
+            before_write("dqkv")
             ops.attn_bwd(qkv[:, :qc], qkv[:, qc:qc + kc], qkv[:, qc + kc:], o2, do2, A["lse"][l], cu, max_len, Hq, Hkv, D,
                          dqkv[:, :qc], dqkv[:, qc:qc + kc], dqkv[:, qc + kc:], workspace=self.attn_ws)
             ops.rope_(dqkv, self.cos, self.sin, pos, Hq + Hkv, D, backward=True)
-            G(ops.TN, dqkv, x1, out=W["d_qkv"], residual=W["d_qkv"] if acc else None)
+            WG(("dqkv",), dqkv, x1, W["d_qkv"])
             G(ops.NN, dqkv, W["qkv"], out=dx)
+            before_write(dh_next_name)
             ops.rmsnorm_bwd(dx, h, W["n1"], sl(A["rstd1"][l]), dres=dh, dx=dh_next, dw=W["d_n1"], accumulate_dw=acc, workspace=self.norm_ws)
             dh, dh_next = dh_next, dh
+            dh_name, dh_next_name = dh_next_name, dh_name
             if last_micro:
                 self._reduce_scatter_unit(1 + l)
         if first_micro:
@@ -528,6 +600,11 @@ class ShardedLlamaEngine:
         ops.embed_bwd(ids, dh, self.G["model.embed_tokens.weight"], accumulate=True, workspace=self.embed_ws)
         if last_micro:
             self._reduce_scatter_unit(0)
+        if self._wg_on and self._wg_last is not None:
+            # join: whatever follows on the compute stream (the next forward overwrites the saved activations and the logits buffer the
+            # wgrad GEMMs read; gradient accumulation / hooks read the flat gradient buffers) is ordered after the last wgrad GEMM
+            st.wait(self._wg_last)
+            self._wg_pending.clear()
         self._grads_dirty = True
 
     # ------------------------------------------------------------------ grad-norm, clip, AdamW, parameter all-gather
@@ -574,8 +651,7 @@ class ShardedLlamaEngine:
                     self.ev_opt[ui] = ev
                 self._all_gather_unit(ui)
 
-        import os as _os2
-        if st.cuda and _os2.environ.get("B200_OPT_OVERLAP", "1") != "0":
+        if self.opt_overlap:
             # The HBM-bound optimizer sweep runs on its own stream, unit by unit in forward order: the next step's forward (tensor-bound)
             # starts as soon as the first units are updated and overlaps the rest (per-unit events gate each layer).
             ready = st.event()

@@ -32,7 +32,9 @@ const char* b200_last_error(void);
 int b200_abi_version(void);
 /* 0 when the current device is sm_100 (B200); B200_ERR_UNSUPPORTED otherwise. */
 int b200_device_check(void);
-/* debug options; "attn_impl": 1 = tcgen05/TMEM attention (default), 0 = mma.sync v1 kernels (bisecting only). */
+/* options; "attn_impl": 1 = tcgen05/TMEM attention (default), 0 = mma.sync v1 kernels (bisecting only); "attn_fwd_variant", "gemm_bn",
+ * "gemm_2cta": kernel selection for A/B runs; "side_blocks_per_sm": k > 0 caps b200_adamw_step / b200_sumsq_bf16 at k 256-thread CTAs per
+ * SM so that they co-reside with a GEMM CTA when issued on a side stream (0 = full occupancy). */
 int b200_set_option(const char* name, int value);
 
 /* ---- dense contractions: nn.Linear fwd/dgrad/wgrad (components/models/llama/model.py:113-115,151,170,511)
