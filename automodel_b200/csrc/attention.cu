@@ -237,24 +237,32 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const __nv_bfloat16* __re
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-// delta[h, t] = sum_d dO[t,h,d] * O[t,h,d]
+// delta[h, t] = sum_d dO[t,h,d] * O[t,h,d].   D/8 lanes per (t, h) row, one 16-byte load of each operand per lane.
 __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                                                         float* __restrict__ delta, int64_t ldo, int64_t lddo, int Hq, int D, int T) {
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per (t, h)
-  const int lane = threadIdx.x & 31;
-  if (gw >= T * Hq) return;
-  const int t = gw / Hq, h = gw % Hq;
-  const __nv_bfloat16* a = o + static_cast<int64_t>(t) * ldo + h * D;
-  const __nv_bfloat16* b = dout + static_cast<int64_t>(t) * lddo + h * D;
+  const int lpr = D >> 3;                                   // lanes per row: 16 (D = 128) or 8 (D = 64)
+  const int64_t gt = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t r = gt / lpr;                               // row = t * Hq + h
+  const int c = static_cast<int>(gt - r * lpr);
   float s = 0.f;
-  for (int i = lane * 2; i < D; i += 64) {
-    const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + i));
-    const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(b + i));
-    s += x.x * y.x + x.y * y.y;
-  }
+  const bool live = r < static_cast<int64_t>(T) * Hq;
+  int t = 0, h = 0;
+  if (live) {
+    t = static_cast<int>(r / Hq);
+    h = static_cast<int>(r - static_cast<int64_t>(t) * Hq);
+    const uint4 a = *reinterpret_cast<const uint4*>(o + static_cast<int64_t>(t) * ldo + h * D + c * 8);
+    const uint4 b = *reinterpret_cast<const uint4*>(dout + static_cast<int64_t>(t) * lddo + h * D + c * 8);
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-  if (lane == 0) delta[static_cast<int64_t>(h) * T + t] = s;
+    for (int e = 0; e < 4; ++e) {
+      const float2 x = __bfloat1622float2(pa[e]);
+      const float2 y = __bfloat1622float2(pb[e]);
+      s += x.x * y.x + x.y * y.y;
+    }
+  }
+  for (int off = lpr >> 1; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);   // lpr is a power of two <= 32
+  if (live && c == 0) delta[static_cast<int64_t>(h) * T + t] = s;
 }
 
 // One CTA per (kv tile of 64 rows, kv head, sequence).  Loops over the q heads of the GQA group and the q tiles at or
@@ -450,8 +458,8 @@ __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __res
 
 // ------------------------------------------------------------------------------------------------ host
 int attn_delta_launch(const void* o, const void* dout, float* delta, int64_t ldo, int64_t lddo, int Hq, int D, int T, cudaStream_t st) {
-  const int64_t warps = static_cast<int64_t>(T) * Hq;
-  attn_delta_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(o),
+  const int64_t threads = static_cast<int64_t>(T) * Hq * (D / 8);
+  attn_delta_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(o),
                                                                                 static_cast<const __nv_bfloat16*>(dout), delta, ldo, lddo, Hq, D, T);
   B200_CHECK_LAUNCH("attn_delta");
   return 0;
@@ -514,12 +522,7 @@ static int attn_bwd_launch(const void* q, const void* k, const void* v, const vo
   float* delta = dq_acc + static_cast<size_t>(T) * Hq * D;
   cudaError_t e = cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(T) * Hq * D * sizeof(float), st);
   if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "attn_bwd memset: %s", cudaGetErrorString(e));
-  {
-    const int64_t warps = static_cast<int64_t>(T) * Hq;
-    attn_delta_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, st>>>(
-        static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(dout), delta, ldo, lddo, Hq, D, T);
-    B200_CHECK_LAUNCH("attn_delta");
-  }
+  if (int rc = attn_delta_launch(o, dout, delta, ldo, lddo, Hq, D, T, st)) return rc;
   dim3 grid((max_len + 63) / 64, Hkv, nseq);
   kern<<<grid, 128, SMEM, st>>>(static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
                                 static_cast<const __nv_bfloat16*>(v), static_cast<const __nv_bfloat16*>(dout), lse, delta, dq_acc,

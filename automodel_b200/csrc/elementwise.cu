@@ -303,52 +303,76 @@ int rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd,
   return set_error(B200_ERR_UNSUPPORTED, "rmsnorm: hidden size %d not in {256,512,1024,2048,4096,8192}", cols);
 }
 
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }          // low / high bf16 of a packed word
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_pair(float lo, float hi) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+__device__ __forceinline__ void round_pair(float& lo, float& hi) {  // (lo, hi) -> bf16 -> fp32: one packed cvt + two bit ops
+  const uint32_t u = pack_pair(lo, hi);
+  lo = bf_lo(u);
+  hi = bf_hi(u);
+}
+
 // ---------------------------------------------------------------------------------------------- RoPE
-// In place on the q and k heads of a token-major buffer (row pitch ld elements).  One thread: 8 elements of the first
-// half of a head and the matching 8 of the second half.  sign=+1 forward, -1 backward (the adjoint rotation).
-__global__ void __launch_bounds__(256) rope_kernel(__nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ cos_t,
+// In place on the q and k heads of a token-major buffer (row pitch ld elements).  One CTA per token, one thread per (head, 16-byte
+// chunk of the first half of the head) and the matching chunk of the second half: the position and the 2*head_dim table entries are
+// shared by every head of the token (L1 hits after the first warp), indices need no 64-bit division, and ~2000 threads per SM each keep
+// two 16-byte loads of q/k in flight.  sign=+1 forward, -1 backward (the adjoint rotation).
+__global__ void __launch_bounds__(320, 4) rope_kernel(__nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ cos_t,
                                                   const __nv_bfloat16* __restrict__ sin_t, const int* __restrict__ pos,
-                                                  int tokens, int heads, int head_dim, int ld, float sign) {
+                                                  int heads, int head_dim, int ld, float sign) {
   const int cpr = head_dim / 16;  // 16B chunks per half head
-  const int64_t total = static_cast<int64_t>(tokens) * heads * cpr;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cpr);
-    const int h = static_cast<int>((i / cpr) % heads);
-    const int t = static_cast<int>(i / (static_cast<int64_t>(cpr) * heads));
-    const int p = pos[t];
-    __nv_bfloat16* base = qk + static_cast<size_t>(t) * ld + h * head_dim + c * 8;
-    const __nv_bfloat16* cb = cos_t + static_cast<size_t>(p) * head_dim + c * 8;
-    const __nv_bfloat16* sb = sin_t + static_cast<size_t>(p) * head_dim + c * 8;
-    float x1[8], x2[8], c1[8], s1[8], c2[8], s2[8], o1[8], o2[8];
-    unpack8(*reinterpret_cast<const uint4*>(base), x1);
-    unpack8(*reinterpret_cast<const uint4*>(base + head_dim / 2), x2);
-    unpack8(*reinterpret_cast<const uint4*>(cb), c1);
-    unpack8(*reinterpret_cast<const uint4*>(sb), s1);
-    unpack8(*reinterpret_cast<const uint4*>(cb + head_dim / 2), c2);
-    unpack8(*reinterpret_cast<const uint4*>(sb + head_dim / 2), s2);
+  const int items = heads * cpr;
+  const int t = blockIdx.x;
+  const int p = pos[t];
+  __nv_bfloat16* row = qk + static_cast<size_t>(t) * ld;
+  const __nv_bfloat16* ct = cos_t + static_cast<size_t>(p) * head_dim;
+  const __nv_bfloat16* st = sin_t + static_cast<size_t>(p) * head_dim;
+  for (int w = threadIdx.x; w < items; w += blockDim.x) {
+    const int h = w / cpr;
+    const int c = w - h * cpr;
+    __nv_bfloat16* base = row + h * head_dim + c * 8;
+    const __nv_bfloat16* cb = ct + c * 8;
+    const __nv_bfloat16* sb = st + c * 8;
+    // operands stay packed (bf16x2 words) until the element pair that needs them: 24 registers of inputs instead of 48
+    const uint4 X1 = *reinterpret_cast<const uint4*>(base), X2 = *reinterpret_cast<const uint4*>(base + head_dim / 2);
+    const uint4 C1 = __ldg(reinterpret_cast<const uint4*>(cb)), S1 = __ldg(reinterpret_cast<const uint4*>(sb));
+    const uint4 C2 = __ldg(reinterpret_cast<const uint4*>(cb + head_dim / 2)), S2 = __ldg(reinterpret_cast<const uint4*>(sb + head_dim / 2));
+    const uint32_t* x1w = &X1.x; const uint32_t* x2w = &X2.x;
+    const uint32_t* c1w = &C1.x; const uint32_t* s1w = &S1.x; const uint32_t* c2w = &C2.x; const uint32_t* s2w = &S2.x;
+    uint4 O1, O2;
+    uint32_t* o1w = &O1.x; uint32_t* o2w = &O2.x;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < 4; ++e) {
       // forward : out1 = x1*cos - x2*sin ; out2 = x2*cos + x1*sin      (q*cos + rotate_half(q)*sin)
       // backward: out1 = x1*cos + x2*sin ; out2 = x2*cos - x1*sin      (adjoint)
       // forward uses sin at the OUTPUT index; the adjoint uses sin at the INPUT index of the rotated term.
-      const float sa = sign > 0.f ? s1[e] : s2[e];
-      const float sb2 = sign > 0.f ? s2[e] : s1[e];
-      o1[e] = bf16_round(x1[e] * c1[e]) - sign * bf16_round(x2[e] * sa);
-      o2[e] = bf16_round(x2[e] * c2[e]) + sign * bf16_round(x1[e] * sb2);
+      const float x1l = bf_lo(x1w[e]), x1h = bf_hi(x1w[e]), x2l = bf_lo(x2w[e]), x2h = bf_hi(x2w[e]);
+      const uint32_t saw = sign > 0.f ? s1w[e] : s2w[e], sbw = sign > 0.f ? s2w[e] : s1w[e];
+      float a_l = x1l * bf_lo(c1w[e]), a_h = x1h * bf_hi(c1w[e]);       // x1*cos
+      float b_l = x2l * bf_lo(saw), b_h = x2h * bf_hi(saw);             // x2*sin
+      float c_l = x2l * bf_lo(c2w[e]), c_h = x2h * bf_hi(c2w[e]);       // x2*cos
+      float d_l = x1l * bf_lo(sbw), d_h = x1h * bf_hi(sbw);             // x1*sin
+      round_pair(a_l, a_h); round_pair(b_l, b_h); round_pair(c_l, c_h); round_pair(d_l, d_h);   // each product is a materialised bf16 tensor
+      o1w[e] = pack_pair(a_l - sign * b_l, a_h - sign * b_h);
+      o2w[e] = pack_pair(c_l + sign * d_l, c_h + sign * d_h);
     }
-    *reinterpret_cast<uint4*>(base) = pack8(o1);
-    *reinterpret_cast<uint4*>(base + head_dim / 2) = pack8(o2);
+    *reinterpret_cast<uint4*>(base) = O1;
+    *reinterpret_cast<uint4*>(base + head_dim / 2) = O2;
   }
 }
 
 int rope_inplace(void* qk, const void* cos_t, const void* sin_t, const int* pos, int tokens, int heads, int head_dim, int ld,
                  int backward, cudaStream_t st) {
   if (head_dim % 16 != 0 || ld % 8 != 0) return set_error(B200_ERR_ARG, "rope: head_dim %% 16 and ld %% 8 required");
-  const int64_t total = static_cast<int64_t>(tokens) * heads * (head_dim / 16);
-  rope_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>(static_cast<__nv_bfloat16*>(qk), static_cast<const __nv_bfloat16*>(cos_t),
-                                                       static_cast<const __nv_bfloat16*>(sin_t), pos, tokens, heads, head_dim, ld,
-                                                       backward ? -1.f : 1.f);
+  if (tokens <= 0 || heads <= 0) return 0;
+  const int items = heads * (head_dim / 16);
+  int threads = (items + 31) / 32 * 32;
+  if (threads > 320) threads = 320;
+  rope_kernel<<<tokens, threads, 0, st>>>(static_cast<__nv_bfloat16*>(qk), static_cast<const __nv_bfloat16*>(cos_t),
+                                          static_cast<const __nv_bfloat16*>(sin_t), pos, heads, head_dim, ld, backward ? -1.f : 1.f);
   B200_CHECK_LAUNCH("rope");
   return 0;
 }
