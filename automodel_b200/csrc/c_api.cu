@@ -65,6 +65,7 @@ static int g_attn_impl = 1;
 extern int forced_bn;
 extern int use_pair;
 extern int side_blocks_per_sm;
+namespace pair { extern int sched_mode; }
 
 // ---------------------------------------------------------------- cuBLASLt comparator (bench / tests only)
 int gemm_bf16_cublaslt(int kind, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K, void* ws,
@@ -132,6 +133,7 @@ int b200_set_option(const char* name, int value) {
   if (name && !strcmp(name, "attn_fwd_variant")) { g_attn_fwd_variant = value; return 0; }
   if (name && !strcmp(name, "gemm_bn")) { b200::forced_bn = value; return 0; }
   if (name && !strcmp(name, "gemm_2cta")) { b200::use_pair = value; return 0; }
+  if (name && !strcmp(name, "gemm_sched")) { b200::pair::sched_mode = value; return 0; }
   if (name && !strcmp(name, "side_blocks_per_sm")) { b200::side_blocks_per_sm = value; return 0; }
   return set_error(B200_ERR_ARG, "unknown option %s", name ? name : "(null)");
 }

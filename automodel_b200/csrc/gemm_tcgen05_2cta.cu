@@ -7,6 +7,14 @@
 // Roles per CTA: warp0 TMA producer (own A rows + own B half, signalling the LEADER's full barrier), warp1 of the leader
 // issues the MMAs and multicasts the commits (smem-slot release, accumulator-ready) to both CTAs, warp2 TMEM allocator
 // (cta_group::2, both CTAs), warps4-7 epilogue of the CTA's own 128 accumulator rows (TMEM lanes) -> TMA store.
+// Tile scheduling, two modes (b200_set_option("gemm_sched", 0|1)):
+//   0  static persistent: one cluster per SM pair, cluster c walks tiles c, c + #clusters, ...
+//   1  cluster launch control (Blackwell CLC): the grid has one cluster per tile; a running cluster that finishes a tile cancels a
+//      not-yet-launched cluster with clusterlaunchcontrol.try_cancel and computes that cluster's tile itself.  Tiles therefore flow to
+//      whichever SM pairs are actually available: SMs held by a co-running kernel (NCCL channels, attention CTAs that cover only part
+//      of the GPU, the other stream's GEMM) simply take fewer tiles, and SM pairs freed by another kernel start taking tiles at once
+//      (the hardware launches pending clusters there).  With static striding a cluster whose SM pair is busy elsewhere still owns
+//      1/#clusters of the tiles and finishes them alone at the end.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -35,8 +43,13 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_OFF = STAGES * STAGE_BYTES;
 constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF_BYTES;
 constexpr int BAR_OFF = EPI_OFF + EPI_BYTES;
-constexpr int NUM_BARS = 2 * STAGES + 4 + EPI_WARPS;
-constexpr int DYN_BYTES = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
+constexpr int CLC_SLOTS = 4;                  // in-flight "next tile" responses (the producer asks one tile ahead; the epilogue lags <= 3 tiles)
+constexpr int NUM_BARS = 2 * STAGES + 4 + EPI_WARPS + 2 * CLC_SLOTS;
+constexpr int CLC_RESP_OFF = BAR_OFF + NUM_BARS * 8 + 16;      // 16-byte aligned (BAR_OFF is, NUM_BARS is even)
+constexpr int DYN_BYTES = CLC_RESP_OFF + CLC_SLOTS * 16 + 1024;
+static_assert(NUM_BARS % 2 == 0, "CLC response slots must stay 16-byte aligned");
+// consumers of one CLC response: leader {producer, MMA thread, 4 epilogue warps} + peer {producer, 4 epilogue warps}
+constexpr int CLC_CONSUMERS = (2 + EPI_WARPS) + (1 + EPI_WARPS);
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -92,6 +105,45 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+// arm (arrive + expect `bytes`) the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_expect_tx_remote(uint64_t* bar, uint32_t cta, uint32_t bytes) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [ra], %2;\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(cta), "r"(bytes)
+      : "memory");
+}
+// Ask the hardware for a not-yet-launched cluster of this grid.  The 16-byte response is written to `resp` in EVERY CTA of the
+// cluster and completes 16 transaction bytes on the barrier at `bar`'s offset in every CTA.
+__device__ __forceinline__ void clc_try_cancel_multicast(void* resp, uint64_t* bar) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];" ::"r"(
+                   smem_u32(resp)),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+// Decode a response: linear tile index (= cluster index = first ctaid.x / 2) of the cancelled cluster, or -1 when nothing was left.
+__device__ __forceinline__ int clc_decode(const void* resp) {
+  uint32_t x, valid;
+  asm volatile(
+      "{\n"
+      ".reg .pred p1;\n"
+      ".reg .b128 r;\n"
+      "ld.shared.b128 r, [%2];\n"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n"
+      "selp.u32 %1, 1, 0, p1;\n"
+      "mov.u32 %0, 0;\n"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid::x.b32.b128 %0, r;\n"
+      "}"
+      : "=r"(x), "=r"(valid)
+      : "r"(smem_u32(resp))
+      : "memory");
+  fence_proxy_async_smem();   // this generic-proxy read is ordered before the async-proxy write of the slot's next response
+  return valid ? static_cast<int>(x >> 1) : -1;
+}
+
 struct Sched {
   int tiles_m, tiles_n, total, group_m;
   __device__ __forceinline__ void coords(int t, int& tm, int& tn) const {
@@ -108,7 +160,7 @@ struct Sched {
 template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-                 const __grid_constant__ CUtensorMap tmR, int M, int N, int K, int flags, int group_m) {
+                 const __grid_constant__ CUtensorMap tmR, int M, int N, int K, int flags, int group_m, int use_clc) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
@@ -117,7 +169,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint64_t* epi_bar = bars + 2 * STAGES + 4;
+  uint64_t* clc_full = bars + 2 * STAGES + 4 + EPI_WARPS;                // per CTA: response k has landed in this CTA's slot
+  uint64_t* clc_empty = clc_full + CLC_SLOTS;                           // (used in the leader) every consumer of both CTAs has read it
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
+  uint8_t* clc_resp = smem + CLC_RESP_OFF;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();  // 0 = leader
@@ -146,6 +201,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tmem_empty[i], 2 * EPI_WARPS);  // (used in the leader) epilogue warps of both CTAs
     }
     for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&epi_bar[i], 1);
+    for (int i = 0; i < CLC_SLOTS; ++i) {
+      mbar_init(&clc_full[i], 1);               // armed by the leader's producer (arrive.expect_tx 16, local and remote)
+      mbar_init(&clc_empty[i], CLC_CONSUMERS);
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -158,12 +217,36 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
+  // Next tile of this cluster after its k-th one.  Static: stride by the number of clusters.  CLC: every consumer waits for response k in
+  // its own CTA, decodes it and hands the slot back to the leader (whose producer re-uses it for response k + CLC_SLOTS).
+  auto next_tile = [&](int t, int k) -> int {
+    if (!use_clc) {
+      t += ncl;
+      return t < sched.total ? t : -1;
+    }
+    const int slot = k % CLC_SLOTS;
+    mbar_wait(&clc_full[slot], (k / CLC_SLOTS) & 1);
+    const int nt = clc_decode(clc_resp + slot * 16);
+    mbar_arrive_remote(&clc_empty[slot], 0);
+    return nt;
+  };
+
   if (warp == 0) {
-    // ===================================================== TMA producer (both CTAs)
+    // ===================================================== TMA producer (both CTAs); the leader's also drives the tile scheduler
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = cid; t < sched.total; t += ncl) {
+      int kt = 0;
+      for (int t = cid; t >= 0; t = next_tile(t, kt++)) {
+        if (use_clc && rank == 0) {
+          // ask for the tile after this one now, so the answer is there when this tile's loads have been issued; asking only one tile
+          // ahead keeps a cluster from hoarding tiles it will not reach before others go idle
+          const int slot = kt % CLC_SLOTS;
+          mbar_wait(&clc_empty[slot], ((kt / CLC_SLOTS) & 1) ^ 1);
+          mbar_arrive_expect_tx(&clc_full[slot], 16);
+          mbar_arrive_expect_tx_remote(&clc_full[slot], 1, 16);
+          clc_try_cancel_multicast(clc_resp + slot * 16, &clc_full[slot]);
+        }
         int tm, tn;
         sched.coords(t, tm, tn);
         const int m0 = tm * 2 * BM + rank * BM;        // this CTA's 128 rows of the 256-row tile
@@ -202,7 +285,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int t = cid; t < sched.total; t += ncl, ++iter) {
+      for (int t = cid; t >= 0; t = next_tile(t, iter++)) {
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -237,7 +320,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t epi_phase = 0;
     int chunk_ctr = 0;
     int iter = 0;
-    for (int t = cid; t < sched.total; t += ncl, ++iter) {
+    for (int t = cid; t >= 0; ++iter) {
       int tm, tn;
       sched.coords(t, tm, tn);
       const int m0 = tm * 2 * BM + rank * BM + w * 32, n0 = tn * BN;
@@ -303,6 +386,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);  // the leader's MMA thread owns the accumulator hand-back
+      int nt = 0;
+      if (lane == 0) nt = next_tile(t, iter);
+      t = __shfl_sync(0xffffffffu, nt, 0);
     }
     if (lane == 0) tma_store_wait<0>();
   }
@@ -317,6 +403,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 static int g_sms = 0;
+int sched_mode = 0;   // b200_set_option("gemm_sched", 0 = static persistent (default) | 1 = cluster launch control)
 
 template <bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const CUtensorMap& tR, int M, int N, int K, int flags,
@@ -338,7 +425,9 @@ static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMa
   if (max_ctas > 0 && max_ctas / 2 < clusters) clusters = max_ctas / 2;
   if (tiles < clusters) clusters = tiles;
   if (clusters < 1) clusters = 1;
-  kern<<<2 * clusters, THREADS, DYN_BYTES, stream>>>(tA, tB, tC, tR, M, N, K, flags, group_m);
+  const int use_clc = sched_mode == 1 && max_ctas <= 0;
+  if (use_clc) clusters = tiles;   // one cluster per tile; running clusters cancel and absorb the pending ones
+  kern<<<2 * clusters, THREADS, DYN_BYTES, stream>>>(tA, tB, tC, tR, M, N, K, flags, group_m, use_clc);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "gemm(pair) launch: %s", cudaGetErrorString(e));
   return 0;

@@ -41,6 +41,17 @@ def device_check():
     check(lib().b200_device_check(), "b200_device_check")
 
 
+def _apply_env_options():
+    """A/B switches from the environment (B200_GEMM_SCHED=1: cluster-launch-control tile scheduler of the CTA-pair GEMM)."""
+    import os
+    v = os.environ.get("B200_GEMM_SCHED")
+    if v is not None:
+        set_option("gemm_sched", int(v))
+
+
+_apply_env_options()
+
+
 def gemm(kind, a, b, out=None, residual=None, round_before_add=True, group_m=0, max_ctas=0):
     """kind NT: a[M,K] b[N,K] -> [M,N];  NN: a[M,K] b[K,N];  TN: a[K,M] b[K,N].  Views with a row pitch are fine."""
     _chk2d(a, "a"); _chk2d(b, "b")

@@ -33,7 +33,8 @@ int b200_abi_version(void);
 /* 0 when the current device is sm_100 (B200); B200_ERR_UNSUPPORTED otherwise. */
 int b200_device_check(void);
 /* options; "attn_impl": 1 = tcgen05/TMEM attention (default), 0 = mma.sync v1 kernels (bisecting only); "attn_fwd_variant", "gemm_bn",
- * "gemm_2cta": kernel selection for A/B runs; "side_blocks_per_sm": k > 0 caps b200_adamw_step / b200_sumsq_bf16 at k 256-thread CTAs per
+ * "gemm_2cta": kernel selection for A/B runs; "gemm_sched": 0 = static persistent tile striding (default), 1 = cluster launch control
+ * (clusterlaunchcontrol.try_cancel: running clusters absorb pending tiles) for the CTA-pair GEMM; "side_blocks_per_sm": k > 0 caps b200_adamw_step / b200_sumsq_bf16 at k 256-thread CTAs per
  * SM so that they co-reside with a GEMM CTA when issued on a side stream (0 = full occupancy). */
 int b200_set_option(const char* name, int value);
 

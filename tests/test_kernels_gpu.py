@@ -68,6 +68,25 @@ def test_gemm_exact_small_integers(kind, shape, gemm_2cta):
     assert torch.equal(out, ref), f"mismatch: {(out != ref).sum().item()} of {out.numel()}"
 
 
+@pytest.mark.parametrize("kind,shape", [(ops.NT, (512, 512, 128)), (ops.TN, (1000, 776, 328)), (ops.NN, (4096, 6144, 4096)),
+                                        (ops.NT, (4096, 28672, 4096))])
+def test_gemm_cluster_launch_control_scheduler_exact(kind, shape):
+    """b200_set_option("gemm_sched", 1): one cluster per tile, running clusters absorb pending ones through
+    clusterlaunchcontrol.try_cancel.  Same bit-exact integer check as the static scheduler (ragged and 8B-sized shapes)."""
+    M, N, K = shape
+    g = torch.Generator(device=DEV).manual_seed(1)
+    gen = lambda s: bf(torch.randint(-3, 4, s, device=DEV, generator=g).float())
+    a, b = _gemm_inputs(kind, M, N, K, gen)
+    ref = bf(_gemm_ref(kind, a, b))
+    ops.set_option("gemm_sched", 1)
+    try:
+        out = ops.gemm(kind, a, b)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option("gemm_sched", 0)
+    assert torch.equal(out, ref), f"mismatch: {(out != ref).sum().item()} of {out.numel()}"
+
+
 @pytest.mark.parametrize("kind", [ops.NT, ops.NN, ops.TN])
 def test_gemm_random_and_cublaslt(kind):
     M, N, K = 2048, 1024, 1536
