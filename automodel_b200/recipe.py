@@ -33,6 +33,7 @@ class B200ShardedConfig:
     master_weights: bool = False
     reference_rounding: bool = True  # bf16(bf16(acc) + residual), as the reference's two eager ops
     max_positions: Optional[int] = None
+    activation_checkpointing: bool = False   # same key as FSDP2Config.activation_checkpointing (distributed/config.py:49-136)
 
 
 class _Fwd(torch.autograd.Function):
@@ -212,7 +213,8 @@ class B200ShardedManager:
         od = optimizer_defaults or {}
         eng = ShardedLlamaEngine(cfg.to_dict() if hasattr(cfg, "to_dict") else cfg, dev, process_group=self.pg, max_tokens=self.config.max_tokens,
                                  adam_mode=self.config.adam_mode, master_weights=self.config.master_weights,
-                                 reference_rounding=self.config.reference_rounding, max_positions=self.config.max_positions, ops=self.ops, **od)
+                                 reference_rounding=self.config.reference_rounding, max_positions=self.config.max_positions,
+                                 activation_checkpointing=self.config.activation_checkpointing, ops=self.ops, **od)
         if hasattr(model, "state_dict") and any(True for _ in model.state_dict()):
             sd = {k: v for k, v in model.state_dict().items()}
             if all(getattr(v, "device", torch.device("cpu")).type != "meta" for v in sd.values()):

@@ -129,3 +129,28 @@ def test_world2_gloo_matches_reference_and_single_rank():
     for k, p in eng.state_dict().items():
         worst = max(worst, float(np.abs(p.float().numpy() - params2[k]).max()))
     assert worst <= 2 * 2 * oc["lr"] + 1e-3, worst
+
+
+def test_activation_checkpointing_is_bit_identical():
+    """with activation_checkpointing the layer activations live in one shared buffer set and are recomputed from the
+    saved layer inputs before each layer's backward (distributed/parallelizer.py:237-268 semantics) - same kernels, same values:
+    losses, gradients and updated weights are identical to the run that keeps everything, including with gradient accumulation."""
+    z, meta = load("hd128_fp32")       # this fixture runs two micro-batches per step
+    cfg = model_cfg(meta)
+    oc = meta["optimizer"]
+    engs = []
+    for ac in (False, True):
+        e = ShardedLlamaEngine(cfg, "cpu", max_tokens=meta["config"]["lbs"] * meta["config"]["seq"], lr=oc["lr"], betas=tuple(oc["betas"]), eps=oc["eps"],
+                               weight_decay=oc["weight_decay"], adam_mode=1, ops=cpu_kernels, activation_checkpointing=ac)
+        e.load_state_dict(init_params(meta))
+        engs.append(e)
+    assert engs[1].act["gu"][0] is engs[1].act["gu"][-1] and engs[0].act["gu"][0] is not engs[0].act["gu"][-1]
+    for s in range(2):
+        mbs = [_mb(b) for b in batches(z, meta, s)]
+        assert len(mbs) > 1
+        res = [e.train_step(mbs, meta["max_grad_norm"]) for e in engs]
+        assert float(res[0][0]) == float(res[1][0]) and float(res[0][1]) == float(res[1][1])
+        for k in engs[0].named_grads():
+            assert torch.equal(engs[0].named_grads()[k], engs[1].named_grads()[k]), k
+    for k, p in engs[0].state_dict().items():
+        assert torch.equal(p, engs[1].state_dict()[k]), k
