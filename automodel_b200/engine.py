@@ -19,10 +19,12 @@ Design (B200-first, 180 GB HBM per GPU):
 All device math is in csrc/ (via ops); torch provides memory, streams and torch.distributed only.
 """
 import math
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
 from .layout import LlamaDims, UnitLayout, build_layout, total_params
 
@@ -106,7 +108,6 @@ class ShardedLlamaEngine:
         self.device = torch.device(device)
         self.pg = process_group
         if process_group is not None:
-            import torch.distributed as dist
             self.world = dist.get_world_size(process_group)
             self.rank = dist.get_rank(process_group)
         else:
@@ -114,7 +115,6 @@ class ShardedLlamaEngine:
         # Optional: run the persistent GEMMs on (SMs - comm_sms) CTAs while NCCL kernels overlap them (B200_COMM_SMS, default 0).
         self.comm_sms = 0
         if self.world > 1 and self.device.type == "cuda":
-            import os
             self.comm_sms = int(os.environ.get("B200_COMM_SMS", "0"))  # measured at N=2 (profiles/r1_n2_comm_sms.md): 0 is best
         self.gemm_ctas = 0  # 0 = one CTA per SM
         if self.comm_sms > 0:
@@ -127,24 +127,22 @@ class ShardedLlamaEngine:
         self.round_before_add = bool(reference_rounding)
         self.step_count = 0
         self.streams = _Streams(self.device)
-        import os as _os0
         # Weight-gradient GEMMs on their own stream: they are off the dgrad dependency chain, so they fill the tensor pipes while the
         # chain runs its HBM-bound kernels (SwiGLU', RMSNorm', RoPE', attention pre/post passes) and the tail waves of the dgrad GEMMs.
         # Default: on for one GPU (measured +2.3..3.4 %); with N > 1 it is opt-in until it has been measured next to the NCCL kernels.
-        self._wg_on = self.streams.cuda and _os0.environ.get("B200_WGRAD_STREAM", "1" if self.world == 1 else "0") == "1"
-        self.opt_overlap = self.streams.cuda and _os0.environ.get("B200_OPT_OVERLAP", "1") != "0"   # optimizer sweep on its own stream
+        self._wg_on = self.streams.cuda and os.environ.get("B200_WGRAD_STREAM", "1" if self.world == 1 else "0") == "1"
+        self.opt_overlap = self.streams.cuda and os.environ.get("B200_OPT_OVERLAP", "1") != "0"   # optimizer sweep on its own stream
         self._wg_pending = {}     # tmp buffer name -> event of the last side-stream GEMM that reads it (WAR guard for the next writer)
         self._wg_last = None
         if self.streams.cuda:
             # side-stream HBM-bound sweeps (AdamW, grad-norm partials) leave register/thread room for a co-resident GEMM CTA
-            self.ops.set_option("side_blocks_per_sm", int(_os0.environ.get("B200_SIDE_BLOCKS", "0")))
+            self.ops.set_option("side_blocks_per_sm", int(os.environ.get("B200_SIDE_BLOCKS", "0")))
         bf, dev = torch.bfloat16, self.device
 
         # ---- persistent flat storage
         self.peer = None
         self._rs_started = False
-        import os as _os
-        if self.world > 1 and dev.type == "cuda" and _os.environ.get("B200_PEER_COMM", "0") == "1":
+        if self.world > 1 and dev.type == "cuda" and os.environ.get("B200_PEER_COMM", "0") == "1":
             # NVLink peer-memory data path (csrc/comm.cu): parameters and gradients of all units live in two IPC-exported slabs
             from .peer import Slab, PeerTable
             offs, tot = [], 0
@@ -297,7 +295,6 @@ class ShardedLlamaEngine:
     def _all_gather_unit(self, ui):
         if self.world == 1:
             return
-        import torch.distributed as dist
         st = self.streams
         ev = st.event()
         st.record(ev)                       # shard update (AdamW) issued on the compute stream
@@ -346,7 +343,6 @@ class ShardedLlamaEngine:
                     st.record(done, st.opt)
                     self.ev_rs[ui] = done
             return
-        import torch.distributed as dist
         st = self.streams
         ev = st.event()
         st.record(ev)                       # this unit's gradients are complete on the compute stream
@@ -654,7 +650,6 @@ class ShardedLlamaEngine:
         if fused_norm:
             self._rs_started = False
         if self.world > 1:
-            import torch.distributed as dist
             dist.all_reduce(self.norm_sq, op=dist.ReduceOp.SUM, group=self.pg)
         return self.norm_sq
 
@@ -704,13 +699,11 @@ class ShardedLlamaEngine:
             nsq = self.optimizer_step(max_grad_norm)
             loss = self.loss_dev.clone()
             if self.world > 1:
-                import torch.distributed as dist
                 dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.pg)
             return loss[0], nsq.sqrt()[0]
         if num_label_tokens is None:
             n = sum(int((mb["labels"] != IGNORE_INDEX).sum()) for mb in micro_batches)
             if self.world > 1:
-                import torch.distributed as dist
                 t = torch.tensor([n], dtype=torch.int64, device=self.device)
                 dist.all_reduce(t, group=self.pg)
                 n = int(t.item())
@@ -722,6 +715,5 @@ class ShardedLlamaEngine:
         nsq = self.optimizer_step(max_grad_norm)
         loss = self.loss_dev.clone()
         if self.world > 1:
-            import torch.distributed as dist
             dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.pg)
         return loss[0], nsq.sqrt()[0]
