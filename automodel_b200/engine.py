@@ -415,11 +415,33 @@ class ShardedLlamaEngine:
 
     # ------------------------------------------------------------------ forward + backward of one micro-batch
     def _stage_inputs(self, input_ids, labels, position_ids):
-        """Host int64 [b,S] tensors -> pinned int32 staging -> ONE async H2D copy of [ids | labels | pos | cu_seqlens]."""
+        """Host int64 [b,S] tensors -> pinned int32 staging -> ONE async H2D copy of [ids | labels | pos | cu_seqlens].
+        Tensors already on the engine's device (the recipe moves each batch there before calling the model, train_ft.py:1403-1420)
+        are converted in place on the device: no host round trip unless the batch is packed (position_ids given), where the number of
+        documents and the longest one size the attention grids and must be known on the host."""
         b, S = input_ids.shape
         T = b * S
         if T > self.max_tokens:
             raise ValueError(f"micro-batch of {T} tokens exceeds max_tokens={self.max_tokens}")
+        if self.streams.cuda and input_ids.device == self.device:
+            k = self._in_idx
+            self._in_idx ^= 1
+            devb = self._in_dev[k]
+            devb[0:T].copy_(input_ids.reshape(-1))
+            if labels is None:
+                devb[T:2 * T].fill_(IGNORE_INDEX)
+            else:
+                devb[T:2 * T].copy_(labels.reshape(-1))
+            if position_ids is None:
+                devb[2 * T:3 * T].view(b, S).copy_(torch.arange(S, dtype=torch.int32, device=self.device))
+                devb[3 * T:3 * T + b + 1].copy_(torch.arange(0, T + 1, S, dtype=torch.int32, device=self.device))
+                nseq, max_len = b, S
+            else:
+                cu_np, max_len = cu_seqlens_from_position_ids(position_ids.cpu().numpy())
+                nseq = cu_np.size - 1
+                devb[2 * T:3 * T].copy_(position_ids.reshape(-1))
+                devb[3 * T:3 * T + nseq + 1].copy_(torch.from_numpy(cu_np).to(self.device, non_blocking=True))
+            return (k, T, nseq, max_len)
         if position_ids is None:
             pos_np = np.tile(np.arange(S, dtype=np.int64), (b, 1))
         else:
@@ -432,7 +454,10 @@ class ShardedLlamaEngine:
             self._in_ev[k].synchronize()      # the copy that last used this pinned buffer has completed
         host, devb = self._in_host[k], self._in_dev[k]
         host[0:T].copy_(input_ids.reshape(-1))
-        host[T:2 * T].copy_(labels.reshape(-1))
+        if labels is None:
+            host[T:2 * T].fill_(IGNORE_INDEX)
+        else:
+            host[T:2 * T].copy_(labels.reshape(-1))
         host[2 * T:3 * T].copy_(torch.from_numpy(pos_np).reshape(-1))
         host[3 * T:3 * T + nseq + 1].copy_(torch.from_numpy(cu_np))
         n = 3 * T + nseq + 1
@@ -448,6 +473,16 @@ class ShardedLlamaEngine:
         """Copy one micro-batch to the device ahead of time; pass the returned handle to forward_backward(staged=...).
         At most two micro-batches can be resident (two buffer sets)."""
         return self._stage_inputs(input_ids, labels, position_ids)
+
+    def set_labels(self, handle, labels):
+        """Replace the labels of a staged micro-batch (the recipe pops `labels` from the batch before calling the model and hands them
+        to the loss function instead, train_ft.py:1436-1460)."""
+        k, T, _, _ = handle
+        lab = labels.reshape(-1)
+        if lab.numel() != T:
+            raise ValueError(f"labels have {lab.numel()} tokens, the staged micro-batch {T}")
+        self._in_dev[k][T:2 * T].copy_(lab.to(torch.int32), non_blocking=True)
+        self.h2d_bytes += 0 if lab.device == self.device else T * 4
 
     def forward_backward(self, input_ids, labels, position_ids, num_label_tokens, first_micro=True, last_micro=True, staged=None):
         """One micro-batch.  Loss (already divided by the GLOBAL label-token count, train_ft.py:1449-1473) accumulates in

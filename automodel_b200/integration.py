@@ -1,0 +1,74 @@
+"""Run-time application of INTEGRATION.md to an importable `nemo_automodel` (the reference): registers `distributed.strategy:
+b200_sharded` and routes the grad-clip utility to the sharded flat gradients.  This is the patch a maintainer would commit upstream,
+expressed as monkey-patches so the UNMODIFIED reference recipe can drive this repository's engine:
+
+    import automodel_b200.integration as b200; b200.register()
+    # YAML: distributed: {strategy: b200_sharded, ...}; optimizer: {_target_: automodel_b200.recipe.B200FusedAdamW, ...}
+
+Touch points (reference file:line):
+  * components/distributed/mesh.py:48-52        STRATEGY_MAP gets "b200_sharded" -> B200ShardedConfig
+  * components/distributed/mesh_utils.py:46-113 create_device_mesh builds the FSDP2 mesh (pp, dp_replicate, dp_shard, cp, tp) for it
+  * _transformers/infrastructure.py:152-182     _instantiate_distributed returns a B200ShardedManager for that config
+  * components/training/utils.py:290-359        scale_grads_and_clip_grad_norm dispatches to model.b200_clip_grad_norm
+Host glue only; imports the reference lazily (it is not a dependency of this package).
+"""
+from .recipe import B200ShardedConfig, B200ShardedManager
+
+_registered = False
+
+
+def register(ops=None, device=None):
+    """Idempotent.  `ops` / `device` are test hooks (CPU stand-in kernels); production leaves them None."""
+    global _registered
+    import nemo_automodel.components.distributed.mesh as _mesh
+    import nemo_automodel._transformers.infrastructure as _infra
+    import nemo_automodel.components.training.utils as _tu
+
+    _mesh.STRATEGY_MAP["b200_sharded"] = B200ShardedConfig
+    if _registered:
+        return
+    _registered = True
+
+    import nemo_automodel.components.distributed.mesh_utils as _mu
+    orig_mesh = _mu.create_device_mesh
+
+    def create_device_mesh(distributed_config, **kw):
+        if isinstance(distributed_config, B200ShardedConfig):
+            if (kw.get("tp_size") or 1) > 1 or (kw.get("pp_size") or 1) > 1 or (kw.get("cp_size") or 1) > 1 or (kw.get("ep_size") or 1) > 1:
+                raise ValueError("strategy b200_sharded is data parallel only (tp/pp/cp/ep sizes must be 1)")
+            return _mu._create_fsdp2_device_mesh(dp_size=kw.get("dp_size"), dp_replicate_size=kw.get("dp_replicate_size"), tp_size=1, pp_size=1,
+                                                 cp_size=1, ep_size=1, world_size=kw["world_size"], backend=distributed_config.backend)
+        return orig_mesh(distributed_config, **kw)
+
+    _mu.create_device_mesh = create_device_mesh
+
+    orig_inst = _infra._instantiate_distributed
+
+    def _instantiate_distributed(config, mesh):
+        if isinstance(config, B200ShardedConfig):
+            pg = None
+            dm = getattr(mesh, "device_mesh", None)
+            if dm is not None and dm.size() > 1:
+                names = dm.mesh_dim_names or ()
+                pg = dm["dp_shard"].get_group() if "dp_shard" in names else dm.get_group()
+            return B200ShardedManager(config, process_group=pg, device=device, ops=ops)
+        return orig_inst(config, mesh)
+
+    _infra._instantiate_distributed = _instantiate_distributed
+
+    orig_clip = _tu.scale_grads_and_clip_grad_norm
+
+    def scale_grads_and_clip_grad_norm(max_grad_norm, model_parts, *args, **kwargs):
+        m = model_parts[0] if isinstance(model_parts, (list, tuple)) else model_parts
+        if hasattr(m, "b200_clip_grad_norm"):
+            return m.b200_clip_grad_norm(max_grad_norm)
+        return orig_clip(max_grad_norm, model_parts, *args, **kwargs)
+
+    _tu.scale_grads_and_clip_grad_norm = scale_grads_and_clip_grad_norm
+    # modules that imported the symbol by name keep their own reference: rebind the recipe's
+    try:
+        import nemo_automodel.recipes.llm.train_ft as _ft
+        if getattr(_ft, "scale_grads_and_clip_grad_norm", None) is orig_clip:
+            _ft.scale_grads_and_clip_grad_norm = scale_grads_and_clip_grad_norm
+    except Exception:  # the recipe module is optional at registration time
+        pass

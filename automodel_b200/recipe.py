@@ -15,6 +15,7 @@ Mirrors the reference's extension points for this path (INTEGRAT
 
 Host glue only: every device operation goes through ShardedLlamaEngine -> the C ABI.
 """
+import weakref
 from dataclasses import dataclass
 from types import SimpleNamespace
 from typing import Optional
@@ -34,6 +35,7 @@ class B200ShardedConfig:
     reference_rounding: bool = True  # bf16(bf16(acc) + residual), as the reference's two eager ops
     max_positions: Optional[int] = None
     activation_checkpointing: bool = False   # same key as FSDP2Config.activation_checkpointing (distributed/config.py:49-136)
+    backend: str = "nccl"                    # accepted for YAML compatibility (`distributed.backend`); torch.distributed is set up by the recipe
 
 
 class _Fwd(torch.autograd.Function):
@@ -97,6 +99,7 @@ class B200CausalLM(nn.Module):
         self._first_micro = True
         self._last_handle = None
         self._last_shape = None
+        engine._facade = weakref.ref(self)   # lets the optimizer built from `model.parameters()` find the module that owns the step state
         self._anchor = nn.Parameter(torch.zeros((), device=engine.device), requires_grad=True)  # keeps the autograd node alive
         # HF-named parameters as views of the flat buffers; .grad = views of the flat gradient buffers
         self._hf = {}
@@ -123,13 +126,13 @@ class B200CausalLM(nn.Module):
         """FSDPModule API used by get_sync_ctx: False on all but the last micro-batch (defer_fsdp_grad_sync)."""
         self._sync_grads = bool(flag)
 
-    def forward(self, input_ids, position_ids=None, labels=None, attention_mask=None, **_ignored):
+    def forward(self, input_ids, position_ids=None, labels=None, attention_mask=None, logits_to_keep=None, **_ignored):
+        # `logits_to_keep` is part of the HF causal-LM signature; the recipe keeps a non-default loss_fn only for models that accept
+        # it (train_ft.py:1056-1058, _supports_logits_to_keep).  Training always needs every position.
+        if logits_to_keep not in (None, 0):
+            raise NotImplementedError("B200CausalLM computes logits for all positions (logits_to_keep must be None or 0)")
         eng = self.engine
-        if labels is None:
-            labels = torch.full_like(input_ids, IGNORE_INDEX)
-        handle = eng.stage(input_ids.cpu() if input_ids.device.type != "cpu" else input_ids,
-                           labels.cpu() if labels.device.type != "cpu" else labels,
-                           None if position_ids is None else (position_ids.cpu() if position_ids.device.type != "cpu" else position_ids))
+        handle = eng.stage(input_ids, labels, position_ids)   # labels=None: the recipe hands them to the loss function (set_labels)
         self._last_handle, self._last_shape = handle, tuple(input_ids.shape)
         logits = _Fwd.apply(self._anchor, self, handle, input_ids.shape[0], input_ids.shape[1])
         logits._b200_model = self
@@ -168,6 +171,7 @@ class B200MaskedCrossEntropy(nn.Module):
             raise NotImplementedError("mask= is not supported; pre-mask the labels with -100 (what the reference does internally)")
         if num_label_tokens is None:
             num_label_tokens = int((labels != IGNORE_INDEX).sum())
+        model.engine.set_labels(model._last_handle, labels)   # the recipe passes labels to the loss, not to the model
         return _FusedLoss.apply(logits, model, int(num_label_tokens))
 
 
@@ -184,16 +188,24 @@ class B200FusedAdamW(torch.optim.Optimizer):
         self._model = None
 
     def attach(self, model: B200CausalLM):
+        """Optional: the owning module is found through the engine (the recipe builds the optimizer from parameters only)."""
         self._model = model
         return self
+
+    def _owner(self):
+        if self._model is not None:
+            return self._model
+        ref = getattr(self.engine, "_facade", None)
+        return ref() if ref is not None else None
 
     @torch.no_grad()
     def step(self, closure=None):
         g = self.param_groups[0]
         e = self.engine
         e.betas, e.eps, e.wd = tuple(g["betas"]), g["eps"], g["weight_decay"]
-        if self._model is not None:
-            self._model.b200_optimizer_step(lr=g["lr"])
+        owner = self._owner()
+        if owner is not None:
+            owner.b200_optimizer_step(lr=g["lr"])     # uses the max_norm of the preceding clip call and re-arms the accumulation window
         else:
             e.optimizer_step(None, lr=g["lr"])
 

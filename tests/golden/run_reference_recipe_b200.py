@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Drive this repository's `b200_sharded` strategy with the UNMODIFIED reference recipe
+(`TrainFinetuneRecipeForNextTokenPrediction`, /root/reference/nemo_automodel/recipes/llm/train_ft.py) on CPU.
+
+Test infrastructure (needs /root/reference; run as a subprocess by tests/test_reference_dropin.py because tests/golden/_ref_env.py
+patches torch globally).  Same YAML as the fixture generator (tests/golden/gen_fixtures.py) except for exactly the lines
+INTEGRATION.md names: `distributed.strategy: b200_sharded`, the optimizer `_target_`, and optionally the loss `_target_`.
+The engine runs on the CPU stand-in kernels (tests/cpu_kernels.py): what is under test is the boundary - that the reference's own
+setup(), data loader, gradient-accumulation loop, loss, clip utility, optimizer/scheduler calls and metric logging work against the
+facade unchanged and reproduce the curve the reference produced with FSDP2.
+
+usage: run_reference_recipe_b200.py <fixture name> <reference_loss|fused_loss> <max steps>   -> one JSON line on stdout
+"""
+import json, os, sys, tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import _ref_env  # noqa: F401,E402
+import torch  # noqa: E402
+
+from tests import cpu_kernels  # noqa: E402
+from tests.golden_utils import load, init_params  # noqa: E402
+import automodel_b200.integration as b200  # noqa: E402
+
+b200.register(ops=cpu_kernels, device=torch.device("cpu"))
+
+from nemo_automodel.components.config._arg_parser import parse_args_and_load_config  # noqa: E402
+from nemo_automodel.recipes.llm.train_ft import TrainFinetuneRecipeForNextTokenPrediction  # noqa: E402
+import gen_fixtures as gf  # noqa: E402
+
+
+def main(name, loss_kind, steps):
+    c = dict(gf.CONFIGS[name])
+    c["steps"] = min(int(steps), c["steps"])
+    y = gf.YAML.format(**c)
+    y = y.replace("strategy: fsdp2", "strategy: b200_sharded, max_tokens: %d, reference_rounding: true" % (c["lbs"] * c["seq"]))
+    y = y.replace("_target_: torch.optim.AdamW", "_target_: automodel_b200.recipe.B200FusedAdamW")
+    if loss_kind == "fused_loss":
+        y = y.replace("_target_: nemo_automodel.components.loss.masked_ce.MaskedCrossEntropy", "_target_: automodel_b200.recipe.B200MaskedCrossEntropy")
+    assert "b200_sharded" in y and "B200FusedAdamW" in y
+    with tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False) as f:
+        f.write(y)
+        path = f.name
+    cfg = parse_args_and_load_config(path, argv=[])
+    r = TrainFinetuneRecipeForNextTokenPrediction(cfg)
+    r.setup()
+    model = r.model_parts[0]
+    z, meta = load(name)
+    model.engine.load_state_dict(init_params(meta))     # the snapshot the fixture run started from
+    rec = {"loss": [], "grad_norm": [], "num_label_tokens": [], "ids_match": []}
+    step_i = [0]
+    orig = r._run_train_optim_step
+
+    def spy(batches, max_grad_norm=None):
+        s = step_i[0]
+        rec["ids_match"].append(all(bool((b["input_ids"].numpy() == z[f"batch/{s}/{j}/input_ids"]).all()) for j, b in enumerate(batches)))
+        m = orig(batches, max_grad_norm)
+        rec["loss"].append(float(m.metrics["loss"])); rec["grad_norm"].append(float(m.metrics["grad_norm"]))
+        rec["num_label_tokens"].append(int(m.metrics["num_label_tokens"]))
+        rec["max_grad_norm"] = max_grad_norm
+        step_i[0] += 1
+        return m
+
+    r._run_train_optim_step = spy
+    r.run_train_validation_loop()
+    rec["model_class"] = type(model).__name__
+    rec["optimizer_class"] = type(r.optimizer[0]).__name__
+    rec["loss_class"] = type(r.loss_fn).__name__
+    sys.stdout.write("\nB200_DROPIN_RESULT " + json.dumps(rec) + "\n")
+
+
+if __name__ == "__main__":
+    main(*sys.argv[1:4])
