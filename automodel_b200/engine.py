@@ -106,6 +106,8 @@ class ShardedLlamaEngine:
         self.dims = cfg if isinstance(cfg, LlamaDims) else LlamaDims.from_hf(cfg)
         d = self.dims
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())   # comparable with tensor.device
         self.pg = process_group
         if process_group is not None:
             self.world = dist.get_world_size(process_group)
