@@ -224,6 +224,7 @@ class ShardedLlamaEngine:
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         self.norm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._grads_dirty = False
+        self._unsynced = False    # gradients accumulated but not yet reduce-scattered (backward ran with last_micro=False)
 
     # ------------------------------------------------------------------ parameter plumbing
     def _mk_fused_views(self):
@@ -659,6 +660,7 @@ class ShardedLlamaEngine:
         ops.embed_bwd(ids, dh, self.G["model.embed_tokens.weight"], accumulate=True, workspace=self.embed_ws)
         if last_micro:
             self._reduce_scatter_unit(0)
+        self._unsynced = not last_micro
         if self._wg_on and self._wg_last is not None:
             # join: whatever follows on the compute stream (the next forward overwrites the saved activations and the logits buffer the
             # wgrad GEMMs read; gradient accumulation / hooks read the flat gradient buffers) is ordered after the last wgrad GEMM
@@ -677,6 +679,12 @@ class ShardedLlamaEngine:
         """Global squared gradient norm over the (reduce-scattered) shards -> self.norm_sq (device scalar)."""
         ops = self.ops
         nu = len(self.units)
+        if self._unsynced:
+            # the caller never announced the last micro-batch (recipe without the get_sync_ctx hook, INTEGRATION.md §3): the gradients of
+            # every unit are complete but still local - reduce-scatter them now (correct; only the overlap with the backward is lost)
+            for ui in reversed(range(nu)):
+                self._reduce_scatter_unit(ui)
+            self._unsynced = False
         fused_norm = self._rs_started   # the per-unit partials were already accumulated as each unit's gradients completed
         for ui in range(nu):
             if self.ev_rs[ui] is not None:

@@ -10,6 +10,9 @@ Touch points (reference file:line):
   * components/distributed/mesh_utils.py:46-113 create_device_mesh builds the FSDP2 mesh (pp, dp_replicate, dp_shard, cp, tp) for it
   * _transformers/infrastructure.py:152-182     _instantiate_distributed returns a B200ShardedManager for that config
   * components/training/utils.py:290-359        scale_grads_and_clip_grad_norm dispatches to model.b200_clip_grad_norm
+  * components/distributed/utils.py:222-247     get_sync_ctx also tells a B200CausalLM which micro-batch is the last one (it only does so
+                                                for FSDPModule instances); without it the facade still trains correctly, it just
+                                                reduce-scatters at clip time instead of under the last backward
 Host glue only; imports the reference lazily (it is not a dependency of this package).
 """
 from .recipe import B200ShardedConfig, B200ShardedManager
@@ -17,7 +20,7 @@ from .recipe import B200ShardedConfig, B200ShardedManager
 _registered = False
 
 
-def register(ops=None, device=None):
+def register(ops=None, device=None, patch_sync_ctx=True):
     """Idempotent.  `ops` / `device` are test hooks (CPU stand-in kernels); production leaves them None."""
     global _registered
     import nemo_automodel.components.distributed.mesh as _mesh
@@ -65,10 +68,25 @@ def register(ops=None, device=None):
         return orig_clip(max_grad_norm, model_parts, *args, **kwargs)
 
     _tu.scale_grads_and_clip_grad_norm = scale_grads_and_clip_grad_norm
-    # modules that imported the symbol by name keep their own reference: rebind the recipe's
+
+    import nemo_automodel.components.distributed.utils as _du
+    orig_sync = _du.get_sync_ctx
+
+    def get_sync_ctx(model, is_optim_step, defer_fsdp_grad_sync=True):
+        if hasattr(model, "b200_clip_grad_norm"):
+            model.set_requires_gradient_sync(is_optim_step)   # gradients accumulate unsharded: sync exactly once, on the last micro-batch
+            from contextlib import nullcontext
+            return nullcontext()
+        return orig_sync(model, is_optim_step, defer_fsdp_grad_sync)
+
+    if patch_sync_ctx:
+        _du.get_sync_ctx = get_sync_ctx
+    # modules that imported the symbols by name keep their own reference: rebind the recipe's
     try:
         import nemo_automodel.recipes.llm.train_ft as _ft
         if getattr(_ft, "scale_grads_and_clip_grad_norm", None) is orig_clip:
             _ft.scale_grads_and_clip_grad_norm = scale_grads_and_clip_grad_norm
+        if patch_sync_ctx and getattr(_ft, "get_sync_ctx", None) is orig_sync:
+            _ft.get_sync_ctx = get_sync_ctx
     except Exception:  # the recipe module is optional at registration time
         pass

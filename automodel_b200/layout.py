@@ -38,10 +38,19 @@ class LlamaDims:
             raise ValueError("tie_word_embeddings=True is not supported by the B200 flat layout (Llama-3 is untied)")
         if g("attention_bias", False) or g("mlp_bias", False):
             raise ValueError("attention_bias / mlp_bias are not supported")
+        # RoPE base and scaling as the reference resolves them (components/models/llama/rope_utils.py:90-109): transformers >= 5 keeps both
+        # in `rope_parameters` ({"rope_theta", "rope_type", "factor", ...}); older configs have `rope_theta` + `rope_scaling`.
+        rp = g("rope_parameters")
+        if rp:
+            theta, scaling = rp.get("rope_theta", 10000.0), dict(rp)
+        else:
+            theta, scaling = g("rope_theta", 10000.0) or 10000.0, g("rope_scaling")
+        if (g("partial_rotary_factor", 1.0) or 1.0) != 1.0:
+            raise ValueError("partial_rotary_factor != 1 is not supported")
         return LlamaDims(hidden=hidden, ffn=g("intermediate_size"), layers=g("num_hidden_layers"), heads=heads,
                          kv_heads=g("num_key_value_heads") or heads, head_dim=g("head_dim") or hidden // heads,
-                         vocab=g("vocab_size"), eps=g("rms_norm_eps", 1e-5), rope_theta=g("rope_theta", 10000.0) or 10000.0,
-                         rope_scaling=g("rope_scaling"), max_pos=g("max_position_embeddings", 4096))
+                         vocab=g("vocab_size"), eps=g("rms_norm_eps", 1e-5), rope_theta=theta,
+                         rope_scaling=scaling, max_pos=g("max_position_embeddings", 4096))
 
     @property
     def q_cols(self):

@@ -62,7 +62,7 @@ class _Fwd(torch.autograd.Function):
             buf.copy_(d2 if scale == 1.0 else d2 * scale)
         elif scale != 1.0:
             buf.mul_(scale)
-        eng.backward_from_dlogits(ctx.handle, first_micro=model._first_micro, last_micro=model._sync_grads)
+        eng.backward_from_dlogits(ctx.handle, first_micro=model._first_micro, last_micro=bool(model._sync_grads))
         model._first_micro = False
         return None, None, None, None, None
 
@@ -95,7 +95,7 @@ class B200CausalLM(nn.Module):
         super().__init__()
         self.config = config
         self.engine = engine
-        self._sync_grads = True
+        self._sync_grads = None    # None: nobody told us which micro-batch is the last (no get_sync_ctx hook) -> reduce-scatter lazily
         self._first_micro = True
         self._last_handle = None
         self._last_shape = None

@@ -22,7 +22,7 @@ from tests import cpu_kernels  # noqa: E402
 from tests.golden_utils import load, init_params  # noqa: E402
 import automodel_b200.integration as b200  # noqa: E402
 
-b200.register(ops=cpu_kernels, device=torch.device("cpu"))
+b200.register(ops=cpu_kernels, device=torch.device("cpu"), patch_sync_ctx=os.environ.get("B200_DROPIN_NO_SYNC_HOOK") != "1")
 
 from nemo_automodel.components.config._arg_parser import parse_args_and_load_config  # noqa: E402
 from nemo_automodel.recipes.llm.train_ft import TrainFinetuneRecipeForNextTokenPrediction  # noqa: E402
@@ -32,6 +32,8 @@ import gen_fixtures as gf  # noqa: E402
 def main(name, loss_kind, steps):
     c = dict(gf.CONFIGS[name])
     c["steps"] = min(int(steps), c["steps"])
+    if os.environ.get("B200_DROPIN_GBS"):
+        c["gbs"] = int(os.environ["B200_DROPIN_GBS"])     # more micro-batches per step than the fixture run (gradient accumulation per rank)
     y = gf.YAML.format(**c)
     y = y.replace("strategy: fsdp2", "strategy: b200_sharded, max_tokens: %d, reference_rounding: true" % (c["lbs"] * c["seq"]))
     y = y.replace("_target_: torch.optim.AdamW", "_target_: automodel_b200.recipe.B200FusedAdamW")
@@ -48,12 +50,18 @@ def main(name, loss_kind, steps):
     z, meta = load(name)
     model.engine.load_state_dict(init_params(meta))     # the snapshot the fixture run started from
     rec = {"loss": [], "grad_norm": [], "num_label_tokens": [], "ids_match": []}
+    dump = {}
     step_i = [0]
     orig = r._run_train_optim_step
 
     def spy(batches, max_grad_norm=None):
         s = step_i[0]
-        rec["ids_match"].append(all(bool((b["input_ids"].numpy() == z[f"batch/{s}/{j}/input_ids"]).all()) for j, b in enumerate(batches)))
+        rec["ids_match"].append(all(f"batch/{s}/{j}/input_ids" in z and bool((b["input_ids"].numpy() == z[f"batch/{s}/{j}/input_ids"]).all())
+                                    for j, b in enumerate(batches)))
+        rec.setdefault("num_micro", []).append(len(batches))
+        for j, b in enumerate(batches):
+            dump[f"{s}/{j}/input_ids"] = b["input_ids"].numpy().copy()
+            dump[f"{s}/{j}/labels"] = b["labels"].numpy().copy()
         m = orig(batches, max_grad_norm)
         rec["loss"].append(float(m.metrics["loss"])); rec["grad_norm"].append(float(m.metrics["grad_norm"]))
         rec["num_label_tokens"].append(int(m.metrics["num_label_tokens"]))
@@ -63,6 +71,9 @@ def main(name, loss_kind, steps):
 
     r._run_train_optim_step = spy
     r.run_train_validation_loop()
+    if os.environ.get("B200_DROPIN_DUMP"):   # per-rank record of what the reference's data loader fed (world-size > 1 check)
+        import numpy as np
+        np.savez(os.environ["B200_DROPIN_DUMP"] + f".rank{int(os.environ.get('RANK', '0'))}.npz", **dump)
     rec["model_class"] = type(model).__name__
     rec["optimizer_class"] = type(r.optimizer[0]).__name__
     rec["loss_class"] = type(r.loss_fn).__name__

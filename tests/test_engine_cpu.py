@@ -154,3 +154,22 @@ def test_activation_checkpointing_is_bit_identical():
             assert torch.equal(engs[0].named_grads()[k], engs[1].named_grads()[k]), k
     for k, p in engs[0].state_dict().items():
         assert torch.equal(p, engs[1].state_dict()[k]), k
+
+
+def test_rope_config_resolution_follows_the_reference():
+    """components/models/llama/rope_utils.py:90-109: `rope_parameters` (transformers >= 5: theta and scaling in one dict) wins over the
+    legacy `rope_theta` / `rope_scaling` pair.  A real LlamaConfig and its to_dict() must give the dims the plain dict gives."""
+    import transformers
+    from automodel_b200.engine import _rope_inv_freq
+    base = dict(vocab_size=512, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=1,
+                max_position_embeddings=256, rms_norm_eps=1e-5)
+    legacy = LlamaDims.from_hf(dict(base, rope_theta=500000.0))
+    hf = transformers.LlamaConfig(**base, rope_theta=500000.0)
+    for cfg in (hf, hf.to_dict()):
+        d = LlamaDims.from_hf(cfg)
+        assert d.rope_theta == 500000.0
+        assert torch.equal(_rope_inv_freq(d), _rope_inv_freq(legacy))
+    l3 = {"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0, "original_max_position_embeddings": 64}
+    a = _rope_inv_freq(LlamaDims.from_hf(dict(base, rope_theta=500000.0, rope_scaling=l3)))
+    b = _rope_inv_freq(LlamaDims.from_hf(dict(base, rope_parameters=dict(l3, rope_theta=500000.0))))
+    assert torch.equal(a, b) and not torch.equal(a, _rope_inv_freq(legacy))

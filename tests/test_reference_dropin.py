@@ -40,3 +40,55 @@ def test_reference_recipe_trains_through_b200_strategy(name, loss_kind, steps, l
         assert rec["num_label_tokens"][s] == meta["num_label_tokens"][s]
         assert abs(rec["loss"][s] - meta["loss"][s]) < loss_tol, (s, rec["loss"][s], meta["loss"][s])
         assert abs(rec["grad_norm"][s] - meta["grad_norm"][s]) < 2e-2 * meta["grad_norm"][s], (s, rec["grad_norm"][s], meta["grad_norm"][s])
+
+
+@pytest.mark.parametrize("gbs,sync_hook", [(2, True), (4, True), (4, False)], ids=["ga1", "ga2_sync_hook", "ga2_lazy_reduce_scatter"])
+def test_reference_recipe_world2_equals_single_rank_accumulation(tmp_path, gbs, sync_hook):
+    """Two reference-recipe processes (gloo) over the b200_sharded strategy: the recipe's data-parallel arithmetic - global label-token
+    count, `(local_loss * dp_group_size).backward()`, its loss all-reduce, the clip utility on sharded gradients - must give the step
+    a single rank gives when it accumulates the same micro-batches (what the two ranks were fed is recorded and replayed).
+    With two micro-batches per rank the reduce-scatter must happen once, after the last one: either announced by the recipe's
+    get_sync_ctx (patched to recognise the facade) or, without that hook, performed lazily when the clip utility asks for the norm."""
+    import socket
+    import numpy as np
+    import torch
+    from automodel_b200.engine import ShardedLlamaEngine
+    from tests import cpu_kernels
+    from tests.golden_utils import model_cfg, init_params
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, PYTHONPATH=ROOT, TORCHDYNAMO_DISABLE="1", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                   LOCAL_RANK=str(rank), WORLD_SIZE="2", B200_DROPIN_DUMP=str(tmp_path / "fed"), B200_DROPIN_GBS=str(gbs),
+                   B200_DROPIN_NO_SYNC_HOOK="0" if sync_hook else "1")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "golden", "run_reference_recipe_b200.py"), "hd128_fp32",
+                                       "reference_loss", "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT))
+    recs = []
+    for p in procs:
+        out, err = p.communicate(timeout=900)
+        lines = [l for l in out.splitlines() if l.startswith("B200_DROPIN_RESULT ")]
+        assert p.returncode == 0 and lines, (out[-2000:], err[-4000:])
+        recs.append(json.loads(lines[-1][len("B200_DROPIN_RESULT "):]))
+    assert recs[0]["loss"] == recs[1]["loss"] and recs[0]["grad_norm"] == recs[1]["grad_norm"]
+    assert recs[0]["num_micro"] == [gbs // 2] * len(recs[0]["loss"])
+    fed = [np.load(str(tmp_path / f"fed.rank{r}.npz")) for r in range(2)]
+    assert not np.array_equal(fed[0]["0/0/input_ids"], fed[1]["0/0/input_ids"]), "both ranks were fed the same samples"
+
+    _, meta = load("hd128_fp32")
+    oc = meta["optimizer"]
+    eng = ShardedLlamaEngine(model_cfg(meta), "cpu", max_tokens=meta["config"]["lbs"] * meta["config"]["seq"], lr=oc["lr"], betas=tuple(oc["betas"]),
+                             eps=oc["eps"], weight_decay=oc["weight_decay"], adam_mode=1, ops=cpu_kernels)
+    eng.load_state_dict(init_params(meta))
+    for s in range(len(recs[0]["loss"])):
+        mbs = []
+        for f in fed:
+            j = 0
+            while f"{s}/{j}/input_ids" in f:
+                mbs.append({"input_ids": torch.from_numpy(f[f"{s}/{j}/input_ids"]), "labels": torch.from_numpy(f[f"{s}/{j}/labels"])})
+                j += 1
+        loss, gn = eng.train_step(mbs, meta["max_grad_norm"])
+        assert abs(float(loss) - recs[0]["loss"][s]) < 1e-3, (s, float(loss), recs[0]["loss"][s])
+        assert abs(float(gn) - recs[0]["grad_norm"][s]) < 5e-3 * float(gn), (s, float(gn), recs[0]["grad_norm"][s])
