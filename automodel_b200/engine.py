@@ -271,6 +271,45 @@ class ShardedLlamaEngine:
             t.zero_()
         self.step_count = 0
 
+    # ------------------------------------------------------------------ optimizer state in per-parameter (HF-named) form
+    def gather_optimizer_state(self):
+        """{name: (exp_avg, exp_avg_sq)} as FULL HF-shaped tensors.  World 1: views of the flat shards (live, zero copy).  World N: every
+        unit's shards are all-gathered into temporaries (checkpoint time only; 2 x model size of extra memory)."""
+        self.sync_params()
+        out = {}
+        for ui, u in enumerate(self.units):
+            if self.world == 1:
+                mf, vf = self.m[ui], self.v[ui]
+            else:
+                mf, vf = torch.empty_like(self.p_full[ui]), torch.empty_like(self.p_full[ui])
+                dist.all_gather_into_tensor(mf, self.m[ui].contiguous(), group=self.pg)
+                dist.all_gather_into_tensor(vf, self.v[ui].contiguous(), group=self.pg)
+            for sl in u.slots:
+                out[sl.name] = (mf[sl.offset:sl.offset + sl.numel].view(sl.shape), vf[sl.offset:sl.offset + sl.numel].view(sl.shape))
+        return out
+
+    def load_optimizer_state(self, named, step_count):
+        """Inverse of gather_optimizer_state: copy this rank's slice of every full (exp_avg, exp_avg_sq) into the flat shards."""
+        with torch.no_grad():
+            for ui, u in enumerate(self.units):
+                a, b = u.shard_range(self.rank, self.world)
+                for sl in u.slots:
+                    lo, hi = max(sl.offset, a), min(sl.offset + sl.numel, b)
+                    if lo >= hi or sl.name not in named:
+                        continue
+                    m_src, v_src = named[sl.name]
+                    self.m[ui][lo - a:hi - a].copy_(m_src.reshape(-1)[lo - sl.offset:hi - sl.offset])
+                    self.v[ui][lo - a:hi - a].copy_(v_src.reshape(-1)[lo - sl.offset:hi - sl.offset])
+        self.step_count = int(step_count)
+
+    def refresh_master_(self):
+        """fp32 master copies (if kept) := the current bf16 weights of this rank's shards (after an external in-place weight load)."""
+        if self.master is not None:
+            with torch.no_grad():
+                for ui, u in enumerate(self.units):
+                    a, b = u.shard_range(self.rank, self.world)
+                    self.master[ui].copy_(self.p_full[ui][a:b].float())
+
     def init_random_(self, seed=0, std=0.02):
         """Random init of the metric config, on device: N(0, std) linears/embeddings, ones for norms
         (HF initialize_weights semantics, components/checkpoint/checkpointing.py:574-676).  Same values on every rank."""

@@ -88,6 +88,10 @@ class _FusedLoss(torch.autograd.Function):
         return out, None, None
 
 
+class _Node(nn.Module):
+    """Empty container: one node of the HF module tree the facade mirrors (no forward of its own)."""
+
+
 class B200CausalLM(nn.Module):
     """nn.Module facade over ShardedLlamaEngine with the surface the recipe uses."""
 
@@ -101,26 +105,50 @@ class B200CausalLM(nn.Module):
         self._last_shape = None
         engine._facade = weakref.ref(self)   # lets the optimizer built from `model.parameters()` find the module that owns the step state
         self._anchor = nn.Parameter(torch.zeros((), device=engine.device), requires_grad=True)  # keeps the autograd node alive
-        # HF-named parameters as views of the flat buffers; .grad = views of the flat gradient buffers
+        # HF-named parameters as views of the flat buffers; .grad = views of the flat gradient buffers.  They hang on a skeleton of empty
+        # container modules that mirrors the HF module tree (model.layers.<i>.self_attn.q_proj.weight ...), so named_parameters(),
+        # state_dict() and FQN walkers such as torch.distributed.checkpoint.state_dict.get_model_state_dict (what the reference's
+        # Checkpointer uses, components/checkpoint/stateful_wrappers.py:278) see the names and shapes of the model they replace.
         self._hf = {}
+        grads = engine.named_grads()
         for name, p in engine.state_dict().items():
             param = nn.Parameter(p, requires_grad=True)
-            param.grad = engine.named_grads()[name]
+            param.grad = grads[name]
             param._b200_engine = engine
             self._hf[name] = param
-            self.register_parameter(name.replace(".", "__"), param)
+            node = self
+            *path, leaf = name.split(".")
+            for part in path:
+                if part not in node._modules:
+                    node.add_module(part, _Node())
+                node = node._modules[part]
+            node.register_parameter(leaf, param)
 
     # ---- reference surface
     def named_parameters(self, prefix="", recurse=True, remove_duplicate=True):
-        for name, p in self._hf.items():
-            yield (prefix + ("." if prefix else "") + name, p)
-
-    def parameters(self, recurse=True):
-        for _, p in self.named_parameters():
-            yield p
+        for name, p in super().named_parameters(prefix=prefix, recurse=recurse, remove_duplicate=remove_duplicate):
+            if not name.endswith("_anchor"):
+                yield name, p
 
     def state_dict(self, *a, **k):
-        return {k_: v.detach() for k_, v in self.engine.state_dict().items()}
+        self.engine.sync_params()
+        sd = super().state_dict(*a, **k)
+        sd.pop(k.get("prefix", "") + "_anchor", None)
+        return sd
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        """In-place copy into the flat buffers (from_pretrained / checkpoint resume); optimizer state is untouched."""
+        missing = [n for n in self._hf if n not in state_dict]
+        unexpected = [n for n in state_dict if n not in self._hf and n != "_anchor"]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"B200CausalLM.load_state_dict: missing {missing[:3]} unexpected {unexpected[:3]}")
+        self.engine.sync_params()
+        with torch.no_grad():
+            for n, p in self._hf.items():
+                if n in state_dict:
+                    p.copy_(state_dict[n])
+        self.engine.refresh_master_()
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
     def set_requires_gradient_sync(self, flag: bool, recurse: bool = True):
         """FSDPModule API used by get_sync_ctx: False on all but the last micro-batch (defer_fsdp_grad_sync)."""
@@ -186,6 +214,7 @@ class B200FusedAdamW(torch.optim.Optimizer):
         self.engine = next(iter(engines.values()))
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._model = None
+        self._refresh_state()
 
     def attach(self, model: B200CausalLM):
         """Optional: the owning module is found through the engine (the recipe builds the optimizer from parameters only)."""
@@ -198,6 +227,38 @@ class B200FusedAdamW(torch.optim.Optimizer):
         ref = getattr(self.engine, "_facade", None)
         return ref() if ref is not None else None
 
+    # ---- optimizer state in torch.optim form (what torch.distributed.checkpoint's get/set_optimizer_state_dict and therefore the
+    # reference's Checkpointer read and write, components/checkpoint/stateful_wrappers.py): per-parameter "step" / "exp_avg" /
+    # "exp_avg_sq".  `self.state` must never be empty, or DCP "initialises" it by running a throw-away optimizer.step().
+    def _refresh_state(self):
+        named = self.engine.gather_optimizer_state()
+        self._step_t = torch.tensor(float(self.engine.step_count))   # ONE tensor shared by every parameter's state entry
+        owner = self._owner()
+        by_param = {id(p): n for n, p in owner._hf.items()} if owner is not None else {}
+        for group in self.param_groups:
+            for p in group["params"]:
+                name = by_param.get(id(p))
+                if name is None:
+                    continue
+                m, v = named[name]
+                self.state[p] = {"step": self._step_t, "exp_avg": m, "exp_avg_sq": v}
+
+    def state_dict(self):
+        self._refresh_state()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        owner = self._owner()
+        named, step = {}, self.engine.step_count
+        for n, p in (owner._hf.items() if owner is not None else []):
+            st = self.state.get(p)
+            if st and "exp_avg" in st:
+                named[n] = (st["exp_avg"], st["exp_avg_sq"])
+                step = int(float(st["step"]))
+        self.engine.load_optimizer_state(named, step)
+        self._refresh_state()     # world 1: back to live views of the flat shards
+
     @torch.no_grad()
     def step(self, closure=None):
         g = self.param_groups[0]
@@ -208,6 +269,7 @@ class B200FusedAdamW(torch.optim.Optimizer):
             owner.b200_optimizer_step(lr=g["lr"])     # uses the max_norm of the preceding clip call and re-arms the accumulation window
         else:
             e.optimizer_step(None, lr=g["lr"])
+        self._step_t += 1
 
     def zero_grad(self, set_to_none: bool = True):
         return None  # wgrad epilogues overwrite the flat buffers on the first micro-batch of the next step

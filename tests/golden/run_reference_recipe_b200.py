@@ -40,6 +40,13 @@ def main(name, loss_kind, steps):
     if loss_kind == "fused_loss":
         y = y.replace("_target_: nemo_automodel.components.loss.masked_ce.MaskedCrossEntropy", "_target_: automodel_b200.recipe.B200MaskedCrossEntropy")
     assert "b200_sharded" in y and "B200FusedAdamW" in y
+    ck = os.environ.get("B200_DROPIN_CKPT")     # "<dir>" or "<dir>:<restore_from>": the reference's own Checkpointer, every 2 steps
+    if ck:
+        ck_dir, _, restore = ck.partition(":")
+        y = y.replace("checkpoint: {enabled: false}", "checkpoint: {enabled: true, checkpoint_dir: %s, model_save_format: safetensors, save_consolidated: true%s}"
+                      % (ck_dir, (", restore_from: " + restore) if restore else ""))
+        y = y.replace("ckpt_every_steps: 100000", "ckpt_every_steps: 2")
+        assert "enabled: true" in y and "ckpt_every_steps: 2" in y
     with tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False) as f:
         f.write(y)
         path = f.name
@@ -48,17 +55,21 @@ def main(name, loss_kind, steps):
     r.setup()
     model = r.model_parts[0]
     z, meta = load(name)
-    model.engine.load_state_dict(init_params(meta))     # the snapshot the fixture run started from
-    rec = {"loss": [], "grad_norm": [], "num_label_tokens": [], "ids_match": []}
+    if not (ck and restore):
+        model.engine.load_state_dict(init_params(meta))     # the snapshot the fixture run started from
+    rec = {"loss": [], "grad_norm": [], "num_label_tokens": [], "ids_match": [], "pre_state": []}
     dump = {}
     step_i = [0]
     orig = r._run_train_optim_step
 
     def spy(batches, max_grad_norm=None):
         s = step_i[0]
-        rec["ids_match"].append(all(f"batch/{s}/{j}/input_ids" in z and bool((b["input_ids"].numpy() == z[f"batch/{s}/{j}/input_ids"]).all())
+        rec["ids_match"].append(all(f"batch/{s}/{j}/input_ids" in z and b["input_ids"].shape == z[f"batch/{s}/{j}/input_ids"].shape and bool((b["input_ids"].numpy() == z[f"batch/{s}/{j}/input_ids"]).all())
                                     for j, b in enumerate(batches)))
         rec.setdefault("num_micro", []).append(len(batches))
+        e = model.engine     # exact fingerprints of weights / Adam moments / step counter before this step
+        rec["pre_state"].append([float(sum(p.double().abs().sum() for p in e.p_full)), float(sum(x.double().abs().sum() for x in e.m)),
+                                 float(sum(x.double().abs().sum() for x in e.v)), e.step_count])
         for j, b in enumerate(batches):
             dump[f"{s}/{j}/input_ids"] = b["input_ids"].numpy().copy()
             dump[f"{s}/{j}/labels"] = b["labels"].numpy().copy()
