@@ -20,6 +20,8 @@ def save_checkpoint(engine, path):
     engine.sync_params()
     if engine.device.type == "cuda":
         torch.cuda.synchronize(engine.device)
+    if engine.replica_rank != 0:
+        return       # HSDP: the replicas hold identical shards; replica 0 writes
     if engine.rank == 0:
         sd = {k: v.detach().to("cpu").contiguous() for k, v in engine.state_dict().items()}
         save_file(sd, os.path.join(path, "model.safetensors"), metadata={"format": "pt"})

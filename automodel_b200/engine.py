@@ -98,7 +98,8 @@ class ShardedLlamaEngine:
     exercise the orchestration over gloo without a GPU."""
 
     def __init__(self, cfg, device, process_group=None, max_tokens=4096, lr=1e-5, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1,
-                 adam_mode=0, master_weights=False, ops=None, max_positions=None, reference_rounding=True, activation_checkpointing=False):
+                 adam_mode=0, master_weights=False, ops=None, max_positions=None, reference_rounding=True, activation_checkpointing=False,
+                 replica_group=None):
         if ops is None:
             from . import ops as _ops  # raises if libb200_train.so is missing: no fallback
             ops = _ops
@@ -114,6 +115,12 @@ class ShardedLlamaEngine:
             self.rank = dist.get_rank(process_group)
         else:
             self.world, self.rank = 1, 0
+        # HSDP (reference: dp_replicate_size > 1, mesh (dp_replicate, dp_shard), distributed/mesh_utils.py:116-190): parameters and
+        # optimizer state are sharded inside `process_group` and replicated across `replica_group`; a unit's gradient shard is
+        # all-reduced across the replicas right after its reduce-scatter.
+        self.rpg = replica_group
+        self.replicas = dist.get_world_size(replica_group) if replica_group is not None else 1
+        self.replica_rank = dist.get_rank(replica_group) if replica_group is not None else 0
         # Optional: run the persistent GEMMs on (SMs - comm_sms) CTAs while NCCL kernels overlap them (B200_COMM_SMS, default 0).
         self.comm_sms = 0
         if self.world > 1 and self.device.type == "cuda":
@@ -145,6 +152,8 @@ class ShardedLlamaEngine:
         self.peer = None
         self._rs_started = False
         if self.world > 1 and dev.type == "cuda" and os.environ.get("B200_PEER_COMM", "0") == "1":
+            if self.replicas > 1:
+                raise NotImplementedError("the NVLink peer-memory path is single-box full sharding; use the NCCL path with replica groups")
             # NVLink peer-memory data path (csrc/comm.cu): parameters and gradients of all units live in two IPC-exported slabs
             from .peer import Slab, PeerTable
             offs, tot = [], 0
@@ -370,6 +379,24 @@ class ShardedLlamaEngine:
 
     def _reduce_scatter_unit(self, ui):
         wg = self._wg_last if self._wg_on else None   # the unit's weight gradients written on the wgrad stream
+        if self.world == 1 and self.replicas > 1:
+            # replicas only (no sharding): all-reduce the whole unit across the replicas
+            st = self.streams
+            if st.cuda:
+                ev = st.event()
+                st.record(ev)
+                with torch.cuda.stream(st.comm):
+                    st.wait(ev, st.comm)
+                    st.wait(wg, st.comm)
+                    dist.all_reduce(self.g_full[ui], op=dist.ReduceOp.SUM, group=self.rpg)
+                    self.ops.sumsq_(self.g_full[ui], self.norm_sq, accumulate=self._rs_started)
+                    self._rs_started = True
+                    done = st.event()
+                    st.record(done, st.comm)
+                    self.ev_rs[ui] = done
+            else:
+                dist.all_reduce(self.g_full[ui], op=dist.ReduceOp.SUM, group=self.rpg)
+            return
         if self.world == 1:
             st = self.streams
             if st.cuda:
@@ -409,6 +436,8 @@ class ShardedLlamaEngine:
                 st.wait(ev, st.comm)
                 st.wait(wg, st.comm)
                 dist.reduce_scatter_tensor(self.shard(self.g_full, ui), self.g_full[ui], op=dist.ReduceOp.SUM, group=self.pg)
+                if self.replicas > 1:
+                    dist.all_reduce(self.shard(self.g_full, ui), op=dist.ReduceOp.SUM, group=self.rpg)
                 self.ops.sumsq_(self.shard(self.g_full, ui), self.norm_sq, accumulate=self._rs_started)  # grad-norm partial, off the critical path
                 self._rs_started = True
                 done = st.event()
@@ -417,6 +446,8 @@ class ShardedLlamaEngine:
         else:
             out = torch.empty_like(self.shard(self.g_full, ui))
             dist.reduce_scatter_tensor(out, self.g_full[ui].clone(), op=dist.ReduceOp.SUM, group=self.pg)
+            if self.replicas > 1:
+                dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.rpg)
             self.shard(self.g_full, ui).copy_(out)
 
     def _wait_params(self, ui):
@@ -781,23 +812,25 @@ class ShardedLlamaEngine:
             for i, hd in enumerate(staged):
                 self.forward_backward(None, None, None, num_label_tokens, first_micro=(i == 0), last_micro=(i == len(staged) - 1), staged=hd)
             nsq = self.optimizer_step(max_grad_norm)
-            loss = self.loss_dev.clone()
-            if self.world > 1:
-                dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.pg)
+            loss = self._allreduce_dp(self.loss_dev.clone())
             return loss[0], nsq.sqrt()[0]
         if num_label_tokens is None:
             n = sum(int((mb["labels"] != IGNORE_INDEX).sum()) for mb in micro_batches)
-            if self.world > 1:
-                t = torch.tensor([n], dtype=torch.int64, device=self.device)
-                dist.all_reduce(t, group=self.pg)
-                n = int(t.item())
+            if self.world * self.replicas > 1:
+                n = int(self._allreduce_dp(torch.tensor([n], dtype=torch.int64, device=self.device)).item())
             num_label_tokens = n
         self.loss_dev.zero_()
         for i, mb in enumerate(micro_batches):
             self.forward_backward(mb["input_ids"], mb["labels"], mb.get("position_ids"), num_label_tokens,
                                   first_micro=(i == 0), last_micro=(i == len(micro_batches) - 1))
         nsq = self.optimizer_step(max_grad_norm)
-        loss = self.loss_dev.clone()
-        if self.world > 1:
-            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.pg)
+        loss = self._allreduce_dp(self.loss_dev.clone())
         return loss[0], nsq.sqrt()[0]
+
+    def _allreduce_dp(self, t):
+        """SUM over every data-parallel rank: the shard group, then (HSDP) the replica group."""
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
+        if self.replicas > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.rpg)
+        return t

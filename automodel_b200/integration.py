@@ -49,12 +49,17 @@ def register(ops=None, device=None, patch_sync_ctx=True):
 
     def _instantiate_distributed(config, mesh):
         if isinstance(config, B200ShardedConfig):
-            pg = None
+            pg = rpg = None
             dm = getattr(mesh, "device_mesh", None)
             if dm is not None and dm.size() > 1:
                 names = dm.mesh_dim_names or ()
-                pg = dm["dp_shard"].get_group() if "dp_shard" in names else dm.get_group()
-            return B200ShardedManager(config, process_group=pg, device=device, ops=ops)
+                if "dp_shard" in names:
+                    pg = dm["dp_shard"].get_group() if dm["dp_shard"].size() > 1 else None
+                    if "dp_replicate" in names and dm["dp_replicate"].size() > 1:     # HSDP: distributed.dp_replicate_size
+                        rpg = dm["dp_replicate"].get_group()
+                else:
+                    pg = dm.get_group()
+            return B200ShardedManager(config, process_group=pg, replica_group=rpg, device=device, ops=ops)
         return orig_inst(config, mesh)
 
     _infra._instantiate_distributed = _instantiate_distributed

@@ -57,7 +57,7 @@ class _Fwd(torch.autograd.Function):
         buf = eng.logits[:T]
         d2 = dlogits.reshape(T, -1)
         # the recipe back-propagates local_loss * dp_group_size (train_ft.py:1473) because FSDP2 averages; our reduce-scatter sums
-        scale = 1.0 / max(eng.world, 1)
+        scale = 1.0 / (eng.world * eng.replicas)
         if d2.data_ptr() != buf.data_ptr():
             buf.copy_(d2 if scale == 1.0 else d2 * scale)
         elif scale != 1.0:
@@ -278,8 +278,8 @@ class B200FusedAdamW(torch.optim.Optimizer):
 class B200ShardedManager:
     """`.parallelize(model)` of the new distributed strategy."""
 
-    def __init__(self, config: B200ShardedConfig, process_group=None, device=None, ops=None):
-        self.config, self.pg, self.device, self.ops = config, process_group, device, ops
+    def __init__(self, config: B200ShardedConfig, process_group=None, device=None, ops=None, replica_group=None):
+        self.config, self.pg, self.device, self.ops, self.rpg = config, process_group, device, ops, replica_group
 
     def parallelize(self, model, optimizer_defaults=None):
         cfg = model.config if hasattr(model, "config") else model
@@ -288,7 +288,7 @@ class B200ShardedManager:
         eng = ShardedLlamaEngine(cfg.to_dict() if hasattr(cfg, "to_dict") else cfg, dev, process_group=self.pg, max_tokens=self.config.max_tokens,
                                  adam_mode=self.config.adam_mode, master_weights=self.config.master_weights,
                                  reference_rounding=self.config.reference_rounding, max_positions=self.config.max_positions,
-                                 activation_checkpointing=self.config.activation_checkpointing, ops=self.ops, **od)
+                                 activation_checkpointing=self.config.activation_checkpointing, replica_group=self.rpg, ops=self.ops, **od)
         if hasattr(model, "state_dict") and any(True for _ in model.state_dict()):
             sd = {k: v for k, v in model.state_dict().items()}
             if all(getattr(v, "device", torch.device("cpu")).type != "meta" for v in sd.values()):

@@ -37,6 +37,9 @@ def main(name, loss_kind, steps):
     y = gf.YAML.format(**c)
     y = y.replace("strategy: fsdp2", "strategy: b200_sharded, max_tokens: %d, reference_rounding: true" % (c["lbs"] * c["seq"]))
     y = y.replace("_target_: torch.optim.AdamW", "_target_: automodel_b200.recipe.B200FusedAdamW")
+    if os.environ.get("B200_DROPIN_REPLICATE"):    # HSDP: distributed.dp_replicate_size
+        y = y.replace("dp_size: none", "dp_size: none, dp_replicate_size: " + os.environ["B200_DROPIN_REPLICATE"])
+        assert "dp_replicate_size" in y
     if loss_kind == "fused_loss":
         y = y.replace("_target_: nemo_automodel.components.loss.masked_ce.MaskedCrossEntropy", "_target_: automodel_b200.recipe.B200MaskedCrossEntropy")
     assert "b200_sharded" in y and "B200FusedAdamW" in y
@@ -85,6 +88,7 @@ def main(name, loss_kind, steps):
     if os.environ.get("B200_DROPIN_DUMP"):   # per-rank record of what the reference's data loader fed (world-size > 1 check)
         import numpy as np
         np.savez(os.environ["B200_DROPIN_DUMP"] + f".rank{int(os.environ.get('RANK', '0'))}.npz", **dump)
+    rec["world"], rec["replicas"] = model.engine.world, model.engine.replicas
     rec["model_class"] = type(model).__name__
     rec["optimizer_class"] = type(r.optimizer[0]).__name__
     rec["loss_class"] = type(r.loss_fn).__name__

@@ -173,3 +173,66 @@ def test_rope_config_resolution_follows_the_reference():
     a = _rope_inv_freq(LlamaDims.from_hf(dict(base, rope_theta=500000.0, rope_scaling=l3)))
     b = _rope_inv_freq(LlamaDims.from_hf(dict(base, rope_parameters=dict(l3, rope_theta=500000.0))))
     assert torch.equal(a, b) and not torch.equal(a, _rope_inv_freq(legacy))
+
+
+def _hsdp_worker(rank, port, out_q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=4)
+    # mesh (dp_replicate=2, dp_shard=2): rows are shard groups, columns are replica groups
+    shard_groups = [dist.new_group([0, 1]), dist.new_group([2, 3])]
+    replica_groups = [dist.new_group([0, 2]), dist.new_group([1, 3])]
+    pg, rpg = shard_groups[rank // 2], replica_groups[rank % 2]
+    z, meta = load("hd128_fp32")
+    oc = meta["optimizer"]
+    eng = ShardedLlamaEngine(model_cfg(meta), "cpu", process_group=pg, replica_group=rpg, max_tokens=meta["config"]["seq"], lr=oc["lr"],
+                             betas=tuple(oc["betas"]), eps=oc["eps"], weight_decay=oc["weight_decay"], adam_mode=1, ops=cpu_kernels)
+    assert (eng.world, eng.replicas, eng.rank, eng.replica_rank) == (2, 2, rank % 2, rank // 2)
+    eng.load_state_dict(init_params(meta))
+    res = []
+    for s in range(2):
+        bs = batches(z, meta, s)                       # two micro-batches of one sequence each
+        b = bs[rank % 2]
+        ids = torch.from_numpy(b["input_ids"]).roll(7 * (rank // 2), dims=1)    # replicas see different tokens
+        lab = torch.full_like(ids, -100); lab[:, :-1] = ids[:, 1:]
+        l, g = eng.train_step([{"input_ids": ids, "labels": lab}], meta["max_grad_norm"])
+        res.append((float(l), float(g)))
+    flat = torch.cat([p.float().reshape(-1) for p in eng.state_dict().values()])
+    gathered = [torch.empty_like(flat) for _ in range(4)]
+    dist.all_gather(gathered, flat)
+    if rank == 0:
+        out_q.put((res, all(torch.equal(gathered[0], t) for t in gathered)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_hsdp_2x2_gloo_equals_single_rank_accumulation():
+    """SURVEY §8f N4 (HSDP, reference dp_replicate_size): 2 replicas x 2 shards over gloo.  Gradient shards are reduce-scattered inside
+    the shard group and all-reduced across the replicas; the step equals one rank accumulating the four micro-batches, and all four
+    ranks end with the same parameters."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_hsdp_worker, args=(r, port, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    res, same = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert same, "ranks disagree on the parameters after the step"
+    z, meta = load("hd128_fp32")
+    oc = meta["optimizer"]
+    eng = ShardedLlamaEngine(model_cfg(meta), "cpu", max_tokens=meta["config"]["seq"], lr=oc["lr"], betas=tuple(oc["betas"]), eps=oc["eps"],
+                             weight_decay=oc["weight_decay"], adam_mode=1, ops=cpu_kernels)
+    eng.load_state_dict(init_params(meta))
+    for s in range(2):
+        bs = batches(z, meta, s)
+        mbs = []
+        for rank in range(4):
+            ids = torch.from_numpy(bs[rank % 2]["input_ids"]).roll(7 * (rank // 2), dims=1)
+            lab = torch.full_like(ids, -100); lab[:, :-1] = ids[:, 1:]
+            mbs.append({"input_ids": ids, "labels": lab})
+        l, g = eng.train_step(mbs, meta["max_grad_norm"])
+        assert abs(float(l) - res[s][0]) < 1e-3, (s, float(l), res[s])
+        assert abs(float(g) - res[s][1]) < 5e-3 * float(g), (s, float(g), res[s])

@@ -27,15 +27,19 @@ def _run(name, loss_kind, steps, **extra_env):
 
 
 def _run_world2(name, loss_kind, steps, **extra_env):
-    """Two ranks of the runner over gloo; returns the two result records."""
+    return _run_world(2, name, loss_kind, steps, **extra_env)
+
+
+def _run_world(world, name, loss_kind, steps, **extra_env):
+    """`world` ranks of the runner over gloo; returns their result records."""
     import socket
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]
     procs = []
-    for rank in range(2):
+    for rank in range(world):
         env = dict(os.environ, PYTHONPATH=ROOT, TORCHDYNAMO_DISABLE="1", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
-                   LOCAL_RANK=str(rank), WORLD_SIZE="2", **extra_env)
+                   LOCAL_RANK=str(rank), WORLD_SIZE=str(world), **extra_env)
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "golden", "run_reference_recipe_b200.py"), name, loss_kind, str(steps)],
                                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT))
     recs = []
@@ -70,19 +74,22 @@ def test_reference_recipe_world2_equals_single_rank_accumulation(tmp_path, gbs, 
     a single rank gives when it accumulates the same micro-batches (what the two ranks were fed is recorded and replayed).
     With two micro-batches per rank the reduce-scatter must happen once, after the last one: either announced by the recipe's
     get_sync_ctx (patched to recognise the facade) or, without that hook, performed lazily when the clip utility asks for the norm."""
+    recs = _run_world2("hd128_fp32", "reference_loss", 2, B200_DROPIN_DUMP=str(tmp_path / "fed"), B200_DROPIN_GBS=str(gbs),
+                       B200_DROPIN_NO_SYNC_HOOK="0" if sync_hook else "1")
+    assert recs[0]["loss"] == recs[1]["loss"] and recs[0]["grad_norm"] == recs[1]["grad_norm"]
+    assert recs[0]["num_micro"] == [gbs // 2] * len(recs[0]["loss"])
+    _replay_and_compare(tmp_path, recs, 2)
+
+
+def _replay_and_compare(tmp_path, recs, world):
+    """One rank (CPU stand-in kernels) accumulates every micro-batch the `world` recipe ranks were fed; loss and grad norm must agree."""
     import numpy as np
     import torch
     from automodel_b200.engine import ShardedLlamaEngine
     from tests import cpu_kernels
     from tests.golden_utils import model_cfg, init_params
-
-    recs = _run_world2("hd128_fp32", "reference_loss", 2, B200_DROPIN_DUMP=str(tmp_path / "fed"), B200_DROPIN_GBS=str(gbs),
-                       B200_DROPIN_NO_SYNC_HOOK="0" if sync_hook else "1")
-    assert recs[0]["loss"] == recs[1]["loss"] and recs[0]["grad_norm"] == recs[1]["grad_norm"]
-    assert recs[0]["num_micro"] == [gbs // 2] * len(recs[0]["loss"])
-    fed = [np.load(str(tmp_path / f"fed.rank{r}.npz")) for r in range(2)]
+    fed = [np.load(str(tmp_path / f"fed.rank{r}.npz")) for r in range(world)]
     assert not np.array_equal(fed[0]["0/0/input_ids"], fed[1]["0/0/input_ids"]), "both ranks were fed the same samples"
-
     _, meta = load("hd128_fp32")
     oc = meta["optimizer"]
     eng = ShardedLlamaEngine(model_cfg(meta), "cpu", max_tokens=meta["config"]["lbs"] * meta["config"]["seq"], lr=oc["lr"], betas=tuple(oc["betas"]),
@@ -98,6 +105,15 @@ def test_reference_recipe_world2_equals_single_rank_accumulation(tmp_path, gbs, 
         loss, gn = eng.train_step(mbs, meta["max_grad_norm"])
         assert abs(float(loss) - recs[0]["loss"][s]) < 1e-3, (s, float(loss), recs[0]["loss"][s])
         assert abs(float(gn) - recs[0]["grad_norm"][s]) < 5e-3 * float(gn), (s, float(gn), recs[0]["grad_norm"][s])
+
+
+def test_reference_recipe_hsdp_2x2(tmp_path):
+    """`distributed.dp_replicate_size: 2` on four ranks (the reference's HSDP mesh (dp_replicate, dp_shard) = (2, 2)): the facade shards
+    inside dp_shard, all-reduces gradient shards across dp_replicate, and scales by the recipe's full dp_group_size."""
+    recs = _run_world(4, "hd128_fp32", "reference_loss", 2, B200_DROPIN_DUMP=str(tmp_path / "fed"), B200_DROPIN_GBS="4", B200_DROPIN_REPLICATE="2")
+    assert all((r["world"], r["replicas"]) == (2, 2) for r in recs)
+    assert all(r["loss"] == recs[0]["loss"] and r["grad_norm"] == recs[0]["grad_norm"] for r in recs)
+    _replay_and_compare(tmp_path, recs, 4)
 
 
 def test_reference_checkpointer_saves_and_resumes_the_b200_strategy(tmp_path):
