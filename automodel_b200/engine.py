@@ -499,21 +499,7 @@ class ShardedLlamaEngine:
         if self.streams.cuda and input_ids.device == self.device:
             k = self._in_idx
             self._in_idx ^= 1
-            devb = self._in_dev[k]
-            devb[0:T].copy_(input_ids.reshape(-1))
-            if labels is None:
-                devb[T:2 * T].fill_(IGNORE_INDEX)
-            else:
-                devb[T:2 * T].copy_(labels.reshape(-1))
-            if position_ids is None:
-                devb[2 * T:3 * T].view(b, S).copy_(torch.arange(S, dtype=torch.int32, device=self.device))
-                devb[3 * T:3 * T + b + 1].copy_(torch.arange(0, T + 1, S, dtype=torch.int32, device=self.device))
-                nseq, max_len = b, S
-            else:
-                cu_np, max_len = cu_seqlens_from_position_ids(position_ids.cpu().numpy())
-                nseq = cu_np.size - 1
-                devb[2 * T:3 * T].copy_(position_ids.reshape(-1))
-                devb[3 * T:3 * T + nseq + 1].copy_(torch.from_numpy(cu_np).to(self.device, non_blocking=True))
+            nseq, max_len = self._fill_input_buffer(self._in_dev[k], input_ids, labels, position_ids)
             return (k, T, nseq, max_len)
         if position_ids is None:
             pos_np = np.tile(np.arange(S, dtype=np.int64), (b, 1))
@@ -541,6 +527,27 @@ class ShardedLlamaEngine:
             self.streams.record(ev)
             self._in_ev[k] = ev
         return (k, T, nseq, max_len)
+
+    @staticmethod
+    def _fill_input_buffer(devb, input_ids, labels, position_ids):
+        """[ids | labels | pos | cu_seqlens] (int32) written into `devb` from tensors that already live on its device."""
+        b, S = input_ids.shape
+        T = b * S
+        dev = devb.device
+        devb[0:T].copy_(input_ids.reshape(-1))
+        if labels is None:
+            devb[T:2 * T].fill_(IGNORE_INDEX)
+        else:
+            devb[T:2 * T].copy_(labels.reshape(-1))
+        if position_ids is None:
+            devb[2 * T:3 * T].view(b, S).copy_(torch.arange(S, dtype=torch.int32, device=dev))
+            devb[3 * T:3 * T + b + 1].copy_(torch.arange(0, T + 1, S, dtype=torch.int32, device=dev))
+            return b, S
+        cu_np, max_len = cu_seqlens_from_position_ids(position_ids.cpu().numpy())
+        nseq = cu_np.size - 1
+        devb[2 * T:3 * T].copy_(position_ids.reshape(-1))
+        devb[3 * T:3 * T + nseq + 1].copy_(torch.from_numpy(cu_np).to(dev, non_blocking=True))
+        return nseq, max_len
 
     def stage(self, input_ids, labels, position_ids=None):
         """Copy one micro-batch to the device ahead of time; pass the returned handle to forward_backward(staged=...).

@@ -236,3 +236,27 @@ def test_hsdp_2x2_gloo_equals_single_rank_accumulation():
         l, g = eng.train_step(mbs, meta["max_grad_norm"])
         assert abs(float(l) - res[s][0]) < 1e-3, (s, float(l), res[s])
         assert abs(float(g) - res[s][1]) < 5e-3 * float(g), (s, float(g), res[s])
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_device_side_input_staging_writes_what_host_staging_writes(packed):
+    """ShardedLlamaEngine._fill_input_buffer (batches that already live on the engine's device) against the pinned-host staging path:
+    same [ids | labels | pos | cu_seqlens] words, same (nseq, max_len)."""
+    z, meta = load("hd128_fp32")
+    eng = ShardedLlamaEngine(model_cfg(meta), "cpu", max_tokens=2 * meta["config"]["seq"], ops=cpu_kernels)
+    g = torch.Generator().manual_seed(0)
+    S = meta["config"]["seq"]
+    ids = torch.randint(0, 512, (2, S), generator=g)
+    lab = torch.full_like(ids, -100); lab[:, :-1] = ids[:, 1:]
+    pos = None
+    if packed:
+        pos = torch.stack([torch.cat([torch.arange(100), torch.arange(S - 100)]), torch.arange(S)])
+    k, T, nseq, max_len = eng.stage(ids, lab, pos)
+    want = eng._in_dev[k][:3 * T + nseq + 1].clone()
+    buf = torch.full_like(eng._in_dev[k], 12345)
+    got = ShardedLlamaEngine._fill_input_buffer(buf, ids, lab, pos)
+    assert got == (nseq, max_len)
+    assert torch.equal(buf[:3 * T + nseq + 1], want)
+    buf2 = torch.full_like(buf, 12345)
+    ShardedLlamaEngine._fill_input_buffer(buf2, ids, None, pos)
+    assert (buf2[T:2 * T] == -100).all() and torch.equal(buf2[:T], want[:T])
