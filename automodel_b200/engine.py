@@ -151,7 +151,11 @@ class ShardedLlamaEngine:
         # ---- persistent flat storage
         self.peer = None
         self._rs_started = False
-        if self.world > 1 and dev.type == "cuda" and os.environ.get("B200_PEER_COMM", "0") == "1":
+        # B200_PEER_COMM: "0" NCCL collectives (default) | "1" NVLink peer path for both collectives | "ag" hybrid: NCCL reduce-scatter,
+        # copy-engine all-gather (zero SMs next to the forward GEMMs)
+        peer_mode = os.environ.get("B200_PEER_COMM", "0")
+        self._peer_rs = peer_mode == "1"
+        if self.world > 1 and dev.type == "cuda" and peer_mode in ("1", "ag"):
             if self.replicas > 1:
                 raise NotImplementedError("the NVLink peer-memory path is single-box full sharding; use the NCCL path with replica groups")
             # NVLink peer-memory data path (csrc/comm.cu): parameters and gradients of all units live in two IPC-exported slabs
@@ -415,7 +419,7 @@ class ShardedLlamaEngine:
         st = self.streams
         ev = st.event()
         st.record(ev)                       # this unit's gradients are complete on the compute stream
-        if st.cuda and self.peer is not None:
+        if st.cuda and self.peer is not None and self._peer_rs:
             # 4-byte all-reduce = "unit ui's gradients are complete on every rank"; then ONE kernel pulls this rank's slice from all
             # peers over NVLink, reduces in fp32, writes the bf16 shard in place and accumulates the shard's sum of squares.
             a, b = self.units[ui].shard_range(self.rank, self.world)

@@ -40,7 +40,7 @@ def _worker(rank, world, port, out_q, peer_comm="1"):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("peer_comm", ["1", "0"], ids=["nvlink_peer_path", "nccl_collectives"])
+@pytest.mark.parametrize("peer_comm", ["1", "0", "ag"], ids=["nvlink_peer_path", "nccl_collectives", "nccl_rs_copy_engine_ag"])
 def test_world2_matches_reference_curve(peer_comm):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
