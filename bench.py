@@ -153,6 +153,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--layers", type=int, default=None, help="debug only: fewer layers (result is then NOT the headline metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-api", default="engine", choices=["engine", "facade"],
+                    help="public call timed by the e2e leg: ShardedLlamaEngine.train_step (default) or the reference-facing facade "
+                         "(B200CausalLM -> B200MaskedCrossEntropy -> backward -> clip -> B200FusedAdamW.step, what the reference recipe drives)")
     ap.add_argument("--profile", action="store_true", help="for ncu runs only: 1 warm-up step, no e2e leg, no CPU baseline (numbers printed are NOT bench values)")
     ap.add_argument("--adam-mode", type=int, default=1, help="1 = torch.optim.AdamW bf16 op sequence (reference default optimizer), 0 = fp32 math")
     args = ap.parse_args()
@@ -284,9 +287,33 @@ def main():
 
     # ------------------------------------------------ leg 2: end to end through the public API (`e2e`): pinned host inputs copied
     # every step inside the timed region + device->host read of the step's loss and grad norm
+    if args.e2e_api == "facade":
+        from automodel_b200.recipe import B200CausalLM, B200MaskedCrossEntropy, B200FusedAdamW
+        fac = B200CausalLM(cfg, eng)
+        fac_loss = B200MaskedCrossEntropy()
+        fac_opt = B200FusedAdamW(fac.parameters(), lr=1e-5, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+
+        def e2e_step(mb):
+            # the recipe's sequence (train_ft.py:1436-1473, 1536-1558): model(**batch) without labels, loss_fn(logits, labels,
+            # num_label_tokens), (loss * dp).backward(), clip utility, optimizer.step(), zero_grad()
+            fac.set_requires_gradient_sync(True)
+            out = fac(input_ids=mb["input_ids"])
+            loss = fac_loss(logits=out.logits, labels=mb["labels"], num_label_tokens=n_label)
+            (loss * world).backward()
+            gn_ = fac.b200_clip_grad_norm(1.0)
+            fac_opt.step()
+            fac_opt.zero_grad()
+            tot = loss.detach().clone()
+            if world > 1:
+                dist.all_reduce(tot)
+            return tot, gn_
+    else:
+        def e2e_step(mb):
+            return eng.train_step([mb], 1.0)
+
     eng.h2d_bytes = 0
     for i in range(0 if args.profile else 2):
-        l, g_ = eng.train_step([host[i % nbatch]], 1.0)
+        l, g_ = e2e_step(host[i % nbatch])
         float(l)
     barrier()
     eng.h2d_bytes = 0
@@ -294,7 +321,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(1 if args.profile else args.steps):
-        l, g_ = eng.train_step([host[i % nbatch]], 1.0)
+        l, g_ = e2e_step(host[i % nbatch])
         lv, gv = float(l), float(g_)         # D2H read of the step result (host sync, as the reference recipe does every step)
     eng.sync_params()
     e1.record()
@@ -302,10 +329,10 @@ def main():
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_step = float(e2e_ms.item()) / args.steps
+    e2e_ms_step = float(e2e_ms.item()) / args.steps
     h2d = eng.h2d_bytes // args.steps
-    e2e = {"value": tokens_per_step / (e2e_step / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
-           "ms_per_step": e2e_step, "host_threads": 1}
+    e2e = {"value": tokens_per_step / (e2e_ms_step / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+           "ms_per_step": e2e_ms_step, "host_threads": 1, "api": "ShardedLlamaEngine.train_step" if args.e2e_api == "engine" else "B200CausalLM facade (recipe call sequence)"}
 
     if rank != 0:
         if world > 1:
