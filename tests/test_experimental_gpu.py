@@ -1,0 +1,68 @@
+"""GPU checks of switches that are implemented but were not yet exercised on a B200.  Not part of the default `-m gpu`
+gate: run with B200_TEST_EXPERIMENTAL=1 (first GPU call of the next round), then move what passes into the regular suites."""
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("B200_TEST_EXPERIMENTAL") != "1", reason="set B200_TEST_EXPERIMENTAL=1")]
+
+from automodel_b200 import ops  # noqa: E402
+from automodel_b200.engine import ShardedLlamaEngine  # noqa: E402
+from tests.golden_utils import load, model_cfg, init_params, batches  # noqa: E402
+
+
+def _mb(b):
+    return {"input_ids": torch.from_numpy(b["input_ids"]), "labels": torch.from_numpy(b["labels"])}
+
+
+def _engine(meta, **kw):
+    oc = meta["optimizer"]
+    e = ShardedLlamaEngine(model_cfg(meta), "cuda", max_tokens=meta["config"]["lbs"] * meta["config"]["seq"], lr=oc["lr"], betas=tuple(oc["betas"]),
+                           eps=oc["eps"], weight_decay=oc["weight_decay"], adam_mode=1, **kw)
+    e.load_state_dict(init_params(meta))
+    return e
+
+
+def test_activation_checkpointing_reproduces_the_reference_curve():
+    z, meta = load("tiny_bf16")
+    e = _engine(meta, activation_checkpointing=True)
+    for s in range(10):
+        l, g = e.train_step([_mb(b) for b in batches(z, meta, s)], meta["max_grad_norm"])
+        assert abs(float(l) - meta["loss"][s]) < 1e-3, (s, float(l), meta["loss"][s])
+        assert abs(float(g) - meta["grad_norm"][s]) < 2e-2 * meta["grad_norm"][s]
+
+
+def test_activation_checkpointing_equals_plain_run_at_8b_layer_dims():
+    cfg = {"vocab_size": 32768, "hidden_size": 4096, "intermediate_size": 14336, "num_hidden_layers": 4, "num_attention_heads": 32,
+           "num_key_value_heads": 8, "max_position_embeddings": 8192, "rms_norm_eps": 1e-5, "rope_theta": 500000.0}
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(0, 32768, (1, 4096), generator=g)
+    lab = torch.full_like(ids, -100); lab[:, :-1] = ids[:, 1:]
+    out = []
+    for ac in (False, True):
+        e = ShardedLlamaEngine(cfg, "cuda", max_tokens=4096, lr=1e-5, adam_mode=1, max_positions=4096, activation_checkpointing=ac)
+        e.init_random_(seed=5)
+        e.loss_dev.zero_()
+        e.forward_backward(ids, lab, None, 4095)
+        torch.cuda.synchronize()
+        out.append((float(e.loss_dev[0]), {k: v.clone() for k, v in e.named_grads().items()}))
+        del e
+        torch.cuda.empty_cache()
+    assert out[0][0] == out[1][0]
+    for k, a in out[0][1].items():
+        assert (a.float() - out[1][1][k].float()).norm() <= 5e-2 * a.float().norm() + 1e-12, k
+
+
+def test_clc_gemm_scheduler_inside_the_step():
+    """The whole step with the cluster-launch-control GEMM scheduler, wgrad stream on: same curve as the reference."""
+    z, meta = load("tiny_bf16")
+    ops.set_option("gemm_sched", 1)
+    try:
+        e = _engine(meta)
+        for s in range(5):
+            l, g = e.train_step([_mb(b) for b in batches(z, meta, s)], meta["max_grad_norm"])
+            assert abs(float(l) - meta["loss"][s]) < 1e-3, (s, float(l), meta["loss"][s])
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option("gemm_sched", 0)
