@@ -39,6 +39,8 @@ def _rope_inv_freq(d: LlamaDims) -> torch.Tensor:
     rtype = sc.get("rope_type", sc.get("type", "default"))
     if rtype == "default":
         return inv
+    if rtype != "llama3":
+        raise ValueError(f"rope_type {rtype!r} is not supported (default and llama3 are; rope_utils.py:152-190 of the reference)")
     factor = sc.get("factor", 1.0)
     lo, hi = sc.get("low_freq_factor", 1.0), sc.get("high_freq_factor", 4.0)
     old = sc.get("original_max_position_embeddings", d.max_pos)

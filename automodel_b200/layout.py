@@ -34,6 +34,11 @@ class LlamaDims:
         g = (lambda k, d=None: cfg.get(k, d)) if isinstance(cfg, dict) else (lambda k, d=None: getattr(cfg, k, d))
         heads = g("num_attention_heads")
         hidden = g("hidden_size")
+        mt = g("model_type")
+        if mt not in (None, "llama", "mistral"):
+            raise ValueError(f"model_type {mt!r}: the B200 sharded step implements the Llama decoder (llama, and mistral without sliding window)")
+        if g("sliding_window"):
+            raise ValueError("sliding-window attention is not supported")
         if g("tie_word_embeddings", False):
             raise ValueError("tie_word_embeddings=True is not supported by the B200 flat layout (Llama-3 is untied)")
         if g("attention_bias", False) or g("mlp_bias", False):

@@ -260,3 +260,15 @@ def test_device_side_input_staging_writes_what_host_staging_writes(packed):
     buf2 = torch.full_like(buf, 12345)
     ShardedLlamaEngine._fill_input_buffer(buf2, ids, None, pos)
     assert (buf2[T:2 * T] == -100).all() and torch.equal(buf2[:T], want[:T])
+
+
+def test_unsupported_configs_are_rejected_loudly():
+    base = dict(vocab_size=512, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=1,
+                max_position_embeddings=256, rms_norm_eps=1e-5)
+    from automodel_b200.engine import _rope_inv_freq
+    for bad in (dict(model_type="qwen2"), dict(sliding_window=4096), dict(tie_word_embeddings=True), dict(attention_bias=True), dict(mlp_bias=True)):
+        with pytest.raises(ValueError):
+            LlamaDims.from_hf(dict(base, **bad))
+    with pytest.raises(ValueError):
+        _rope_inv_freq(LlamaDims.from_hf(dict(base, rope_scaling={"rope_type": "yarn", "factor": 4.0})))
+    LlamaDims.from_hf(dict(base, model_type="mistral", sliding_window=None))
