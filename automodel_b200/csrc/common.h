@@ -16,6 +16,7 @@
 
 #define GEMM_FLAG_RESIDUAL 1          // C = acc + R
 #define GEMM_FLAG_ROUND_BEFORE_ADD 2  // C = bf16(acc) + R   (matches the reference's two materialised bf16 ops)
+#define GEMM_FLAG_SWIGLU 4            // NT only, B = [gate; up] rows (N = 2F): C = [gate | up] as usual AND R[M, F] = silu(gate) * up (R is an OUTPUT)
 
 namespace b200 {
 

@@ -391,6 +391,10 @@ int gemm_bf16_tcgen05(int kind, const void* A, int lda, const void* B, int ldb, 
                       int M, int N, int K, int flags, int group_m, int max_ctas, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(B200_ERR_ARG, "gemm: empty problem %dx%dx%d", M, N, K);
   if ((flags & GEMM_FLAG_RESIDUAL) && !R) return set_error(B200_ERR_ARG, "gemm: residual flag without R");
+  if (flags & GEMM_FLAG_SWIGLU) {
+    if (kind != GEMM_NT || (flags & GEMM_FLAG_RESIDUAL) || !R || N % 256 != 0 || M < 256 || !use_pair || forced_bn != 0)
+      return set_error(B200_ERR_UNSUPPORTED, "gemm: the SwiGLU epilogue needs the CTA-pair kernel, kind NT, M >= 256, N = 2F with F %% 128 == 0, R = the [M, F] output");
+  }
   if (use_pair && M >= 256 && N >= 256 && forced_bn == 0)
     return gemm_bf16_tcgen05_pair(kind, A, lda, B, ldb, C, ldc, R, ldr, M, N, K, flags, group_m, max_ctas, stream);
   if (group_m <= 0) group_m = 8;

@@ -7,6 +7,10 @@
 // Roles per CTA: warp0 TMA producer (own A rows + own B half, signalling the LEADER's full barrier), warp1 of the leader
 // issues the MMAs and multicasts the commits (smem-slot release, accumulator-ready) to both CTAs, warp2 TMEM allocator
 // (cta_group::2, both CTAs), warps4-7 epilogue of the CTA's own 128 accumulator rows (TMEM lanes) -> TMA store.
+// Optional SwiGLU epilogue (GEMM_FLAG_SWIGLU, x @ [W_gate; W_up]^T): for column tile j the leader stages W rows j*128.. (gate) and the peer
+// rows F + j*128.. (up) as their halves of B, so the 256 accumulator columns are gate and up of the SAME 128 features side by side; the
+// epilogue stores both (the backward needs them) and also a = bf16(bf16(silu(g)) * u) computed from the rounded values - bit-identical to
+// swiglu_fwd_kernel, without re-reading gu from HBM and with no permutation of the weight rows.
 // Tile scheduling, two modes (b200_set_option("gemm_sched", 0|1)):
 //   0  static persistent: one cluster per SM pair, cluster c walks tiles c, c + #clusters, ...
 //   1  cluster launch control (Blackwell CLC): the grid has one cluster per tile; a running cluster that finishes a tile cancels a
@@ -22,6 +26,8 @@
 
 #include "ptx.cuh"
 #include "common.h"
+
+#pragma nv_diag_suppress 128   // "loop is not reachable": the plain epilogue loop in the SWIGLU instantiation (that branch ends in `continue`)
 
 namespace b200 {
 
@@ -144,6 +150,12 @@ __device__ __forceinline__ int clc_decode(const void* resp) {
   return valid ? static_cast<int>(x >> 1) : -1;
 }
 
+__device__ __forceinline__ float rcp_fast_(float x) {  // same MUFU reciprocal as elementwise.cu's SwiGLU kernel
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct Sched {
   int tiles_m, tiles_n, total, group_m;
   __device__ __forceinline__ void coords(int t, int& tm, int& tn) const {
@@ -157,7 +169,7 @@ struct Sched {
   }
 };
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool SWIGLU>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                  const __grid_constant__ CUtensorMap tmR, int M, int N, int K, int flags, int group_m, int use_clc) {
@@ -189,7 +201,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
-    if (flags & GEMM_FLAG_RESIDUAL) tma_prefetch_desc(&tmR);
+    if (SWIGLU || (flags & GEMM_FLAG_RESIDUAL)) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -250,7 +262,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int tm, tn;
         sched.coords(t, tm, tn);
         const int m0 = tm * 2 * BM + rank * BM;        // this CTA's 128 rows of the 256-row tile
-        const int n0 = tn * BN + rank * (BN / 2);      // this CTA's half of the B rows
+        // this CTA's half of the B rows; SwiGLU: the leader's half is the gate block of feature tile tn, the peer's the matching up block
+        const int n0 = SWIGLU ? tn * (BN / 2) + rank * (N / 2) : tn * BN + rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * STAGE_BYTES;
@@ -329,6 +342,62 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(w * 32) << 16) + acc * BN;
+      if constexpr (SWIGLU) {
+        // columns [0,128) = gate, [128,256) = up of features tn*128 .. tn*128+127.  Per 64-feature chunk: three 32x64 bf16 tiles leave
+        // through the two staging buffers (gate -> C[:, f], up -> C[:, F + f], a -> R[:, f]).
+        const int F = N / 2, f0 = tn * (BN / 2);
+        const bool live = m0 < M;
+        auto put_tile = [&](const uint32_t (&pk)[32], const CUtensorMap* tm, int col) {
+          uint8_t* stg = stg_base + (chunk_ctr & 1) * EPI_BUF_BYTES;
+          ++chunk_ctr;
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          if (live) {
+            uint8_t* row_ptr = stg + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint4 o;
+              o.x = pk[4 * j]; o.y = pk[4 * j + 1]; o.z = pk[4 * j + 2]; o.w = pk[4 * j + 3];
+              *reinterpret_cast<uint4*>(row_ptr + ((j ^ (lane & 7)) << 4)) = o;
+            }
+            fence_proxy_async_smem();
+          }
+          __syncwarp();
+          if (live && lane == 0) tma_store_2d(tm, stg, col, m0);
+          if (lane == 0) tma_store_commit();
+        };
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[64], gp[32], up[32], ap[32];
+          tmem_ld_32x32b_x32(t_row + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld_32x32b_x32(t_row + c * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) gp[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+          put_tile(gp, &tmC, f0 + c * 64);
+          tmem_ld_32x32b_x32(t_row + BN / 2 + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld_32x32b_x32(t_row + BN / 2 + c * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) up[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+          put_tile(up, &tmC, F + f0 + c * 64);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gp[e]));
+            const float2 u = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&up[e]));
+            const float s0 = bf16_round(g.x * rcp_fast_(1.f + __expf(-g.x))), s1 = bf16_round(g.y * rcp_fast_(1.f + __expf(-g.y)));
+            ap[e] = pack_bf16x2(s0 * u.x, s1 * u.y);
+          }
+          put_tile(ap, &tmR, f0 + c * 64);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);
+        int nt = 0;
+        if (lane == 0) nt = next_tile(t, iter);
+        t = __shfl_sync(0xffffffffu, nt, 0);
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 64; ++c, ++chunk_ctr) {
         uint8_t* stg = stg_base + (chunk_ctr & 1) * EPI_BUF_BYTES;
@@ -405,10 +474,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 static int g_sms = 0;
 int sched_mode = 0;   // b200_set_option("gemm_sched", 0 = static persistent (default) | 1 = cluster launch control)
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool SWIGLU = false>
 static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const CUtensorMap& tR, int M, int N, int K, int flags,
                   int group_m, int max_ctas, cudaStream_t stream) {
-  auto kern = gemm_pair_kernel<A_MN, B_MN>;
+  auto kern = gemm_pair_kernel<A_MN, B_MN, SWIGLU>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES);
@@ -447,7 +516,9 @@ int gemm_bf16_tcgen05_pair(int kind, const void* A, int lda, const void* B, int 
   rc = b_mn ? make_tmap_2d_bf16(&tB, B, K, N, ldb, 64, BK) : make_tmap_2d_bf16(&tB, B, N, K, ldb, BK, BN / 2);
   if (rc) return rc;
   if ((rc = make_tmap_2d_bf16(&tC, C, M, N, ldc, 64, 32))) return rc;
-  if (flags & GEMM_FLAG_RESIDUAL) {
+  if (flags & GEMM_FLAG_SWIGLU) {
+    if ((rc = make_tmap_2d_bf16(&tR, R, M, N / 2, ldr, 64, 32))) return rc;    // the activation output a [M, F]
+  } else if (flags & GEMM_FLAG_RESIDUAL) {
     if ((rc = make_tmap_2d_bf16(&tR, R, M, N, ldr, 64, 32))) return rc;
   } else {
     tR = tC;
@@ -459,6 +530,7 @@ int gemm_bf16_tcgen05_pair(int kind, const void* A, int lda, const void* B, int 
     const int tiles_m = (M + 2 * BM - 1) / (2 * BM), tiles_n = (N + BN - 1) / BN;
     group_m = tiles_n > tiles_m ? (tiles_m < 16 ? tiles_m : 16) : 1;
   }
+  if (kind == GEMM_NT && (flags & GEMM_FLAG_SWIGLU)) return launch<false, false, true>(tA, tB, tC, tR, M, N, K, flags, group_m, max_ctas, stream);
   if (kind == GEMM_NT) return launch<false, false>(tA, tB, tC, tR, M, N, K, flags, group_m, max_ctas, stream);
   if (kind == GEMM_NN) return launch<false, true>(tA, tB, tC, tR, M, N, K, flags, group_m, max_ctas, stream);
   if (kind == GEMM_TN) return launch<true, true>(tA, tB, tC, tR, M, N, K, flags, group_m, max_ctas, stream);

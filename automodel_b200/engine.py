@@ -145,6 +145,8 @@ class ShardedLlamaEngine:
         self.opt_overlap = self.streams.cuda and os.environ.get("B200_OPT_OVERLAP", "1") != "0"   # optimizer sweep on its own stream
         self._wg_pending = {}     # tmp buffer name -> event of the last side-stream GEMM that reads it (WAR guard for the next writer)
         self._wg_last = None
+        # B200_FUSE_SWIGLU=1: SwiGLU computed in the epilogue of the gate/up GEMM (b200_gemm_bf16 flag 4) instead of a separate HBM pass
+        self._fuse_swiglu = self.streams.cuda and os.environ.get("B200_FUSE_SWIGLU", "0") == "1" and d.ffn % 128 == 0
         if self.streams.cuda:
             # side-stream HBM-bound sweeps (AdamW, grad-norm partials) leave register/thread room for a co-resident GEMM CTA
             self.ops.set_option("side_blocks_per_sm", int(os.environ.get("B200_SIDE_BLOCKS", "0")))
@@ -642,8 +644,11 @@ class ShardedLlamaEngine:
         ops.attn_fwd(qkv[:, :qc], qkv[:, qc:qc + kc], qkv[:, qc + kc:], cu, max_len, Hq, Hkv, D, out=o2, lse=A["lse"][l])
         G(ops.NT, o2, W["o"], out=h1, residual=h, round_before_add=rba)
         ops.rmsnorm_fwd(h1, W["n2"], d.eps, out=x2, rstd=sl(A["rstd2"][l]))
-        G(ops.NT, x2, W["gu"], out=gu)
-        ops.swiglu_fwd(gu, out=a)
+        if self._fuse_swiglu and T >= 256 and ctas == 0:
+            ops.gemm_swiglu(x2, W["gu"], gu, a)
+        else:
+            G(ops.NT, x2, W["gu"], out=gu)
+            ops.swiglu_fwd(gu, out=a)
         G(ops.NT, a, W["down"], out=sl(A["h"][l + 1]), residual=h1, round_before_add=rba)
 
     def backward_from_dlogits(self, handle, first_micro=True, last_micro=True):

@@ -7,7 +7,7 @@ import torch
 from ._lib import lib, check
 
 NT, NN, TN = 0, 1, 2
-GEMM_RESIDUAL, GEMM_ROUND_BEFORE_ADD = 1, 2
+GEMM_RESIDUAL, GEMM_ROUND_BEFORE_ADD, GEMM_SWIGLU = 1, 2, 4
 
 # number of kernels of THIS library launched so far (bench.py reports the count inside its timed region)
 LAUNCHES = 0
@@ -86,6 +86,32 @@ def gemm(kind, a, b, out=None, residual=None, round_before_add=True, group_m=0, 
 
 
 _lt_ws = {}
+
+
+def gemm_swiglu(x, w_gu, gu=None, a=None):
+    """x[M,K] @ w_gu[2F,K]^T with the SwiGLU epilogue: returns (gu [M,2F] = [gate | up], a [M,F] = silu(gate) * up), both bf16, from ONE
+    GEMM launch (CTA-pair kernel; M >= 256, F % 128 == 0).  Bit-identical to gemm(NT) followed by swiglu_fwd."""
+    _chk2d(x, "x"); _chk2d(w_gu, "w_gu")
+    M, K = x.shape
+    N = w_gu.shape[0]
+    assert w_gu.shape[1] == K and N % 2 == 0
+    if gu is None:
+        gu = torch.empty(M, N, dtype=torch.bfloat16, device=x.device)
+    if a is None:
+        a = torch.empty(M, N // 2, dtype=torch.bfloat16, device=x.device)
+    _chk2d(gu, "gu"); _chk2d(a, "a")
+
+    def launch():
+        check(lib().b200_gemm_bf16(NT, x.data_ptr(), x.stride(0), w_gu.data_ptr(), w_gu.stride(0), gu.data_ptr(), gu.stride(0), a.data_ptr(),
+                                   a.stride(0), M, N, K, GEMM_SWIGLU, 0, 0, _st()), "b200_gemm_bf16(swiglu)")
+
+    if GEMM_TIMER is not None:
+        with GEMM_TIMER(NT, M, N, K):
+            launch()
+    else:
+        launch()
+    _count(1)
+    return gu, a
 
 
 def gemm_cublaslt(kind, a, b, out=None):

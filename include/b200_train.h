@@ -44,12 +44,16 @@ int b200_set_option(const char* name, int value);
  * kind 2 (TN): C[M,N] = A[K,M]^T * B[K,N]      wgrad     dW = dy^T x
  * flags bit0: C = acc + R (R bf16 [M,N], may alias C);  bit1: round acc to bf16 before the add (reference numerics:
  * residual add after the o_proj/down_proj output was materialised, model.py:227,233; also grad accumulation).
- * tcgen05 tensor cores, TMA, TMEM accumulators.  group_m: L2 rasterisation group (0 = default). */
+ * tcgen05 tensor cores, TMA, TMEM accumulators.  group_m: L2 rasterisation group (0 = default).
+ * flags bit 2 (4, experimental): SwiGLU epilogue for kind NT with B = [W_gate; W_up] (N = 2F, F % 128 == 0, M >= 256):
+ * C = [gate | up] as usual and R (an OUTPUT here, [M, F], pitch ldr) = bf16(bf16(silu(gate)) * up)  (model.py:155-170 act_fn(gate) * up).
+ */
 #define B200_GEMM_NT 0
 #define B200_GEMM_NN 1
 #define B200_GEMM_TN 2
 #define B200_GEMM_RESIDUAL 1
 #define B200_GEMM_ROUND_BEFORE_ADD 2
+#define B200_GEMM_SWIGLU 4
 int b200_gemm_bf16(int kind, const void* A, int lda, const void* B, int ldb, void* C, int ldc, const void* R, int ldr,
                    int M, int N, int K, int flags, int group_m, int max_ctas, b200_stream_t stream);
 /* cuBLASLt on the same operands: the bar to beat (bench/tests only, never on the training path). */

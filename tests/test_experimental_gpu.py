@@ -66,3 +66,29 @@ def test_clc_gemm_scheduler_inside_the_step():
         torch.cuda.synchronize()
     finally:
         ops.set_option("gemm_sched", 0)
+
+
+@pytest.mark.parametrize("M,F,K", [(512, 512, 256), (1000, 640, 328), (4096, 14336, 4096)])
+def test_gemm_swiglu_epilogue_is_bit_identical_to_the_two_kernel_path(M, F, K):
+    g = torch.Generator(device="cuda").manual_seed(M + F)
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(2 * F, K, device="cuda", generator=g) * 0.05).bfloat16()
+    gu_ref = ops.gemm(ops.NT, x, w)
+    a_ref = ops.swiglu_fwd(gu_ref)
+    gu, a = ops.gemm_swiglu(x, w)
+    torch.cuda.synchronize()
+    assert torch.equal(gu, gu_ref), int((gu != gu_ref).sum())
+    assert torch.equal(a, a_ref), int((a != a_ref).sum())
+
+
+def test_fused_swiglu_inside_the_step(monkeypatch):
+    monkeypatch.setenv("B200_FUSE_SWIGLU", "1")
+    z, meta = load("tiny_bf16")
+    e = _engine(meta)
+    assert e._fuse_swiglu
+    before = ops.LAUNCHES
+    for s in range(5):
+        l, g = e.train_step([_mb(b) for b in batches(z, meta, s)], meta["max_grad_norm"])
+        assert abs(float(l) - meta["loss"][s]) < 1e-3, (s, float(l), meta["loss"][s])
+    torch.cuda.synchronize()
+    assert ops.LAUNCHES > before

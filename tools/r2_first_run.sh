@@ -3,9 +3,11 @@
 #   gpurun --timeout 600 -- bash tools/r2_first_run.sh
 mkdir -p gpurun_out
 B200_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_experimental_gpu.py -q -m gpu > gpurun_out/r2_experimental.log 2>&1; echo "experimental rc=$?"; tail -3 gpurun_out/r2_experimental.log
-for cfg in "0 engine" "1 engine" "0 facade"; do
+for cfg in "0 engine" "1 engine" "0 facade" "0 engine-swiglu"; do
   set -- $cfg
-  B200_GEMM_SCHED=$1 timeout 200 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --e2e-api $2 > gpurun_out/r2_n1_sched$1_$2.json 2> gpurun_out/r2_n1_sched$1_$2.err
+  fuse=0; api=$2
+  if [ "$2" = "engine-swiglu" ]; then fuse=1; api=engine; fi
+  B200_FUSE_SWIGLU=$fuse B200_GEMM_SCHED=$1 timeout 200 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --e2e-api $api > gpurun_out/r2_n1_sched$1_$2.json 2> gpurun_out/r2_n1_sched$1_$2.err
   python - "$1" "$2" <<'PY'
 import json, sys
 try:
