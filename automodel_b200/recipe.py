@@ -71,10 +71,10 @@ class _FusedLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, model, num_label_tokens):
         eng = model.engine
-        before = eng.loss_dev.clone()
+        eng.loss_dev.zero_()      # one value per call (the recipe sums the micro-batch losses itself); never difference a growing accumulator
         eng.fused_loss(model._last_handle, num_label_tokens)   # logits buffer now holds dlogits for a unit upstream gradient
         ctx.model = model
-        return (eng.loss_dev - before)[0].clone()
+        return eng.loss_dev[0].clone()
 
     @staticmethod
     def backward(ctx, g):
@@ -198,7 +198,7 @@ class B200MaskedCrossEntropy(nn.Module):
         if mask is not None:
             raise NotImplementedError("mask= is not supported; pre-mask the labels with -100 (what the reference does internally)")
         if num_label_tokens is None:
-            num_label_tokens = int((labels != IGNORE_INDEX).sum())
+            num_label_tokens = 1      # reduction="sum" without normalisation, as the reference returns it (masked_ce.py:84-89; validation loop)
         model.engine.set_labels(model._last_handle, labels)   # the recipe passes labels to the loss, not to the model
         return _FusedLoss.apply(logits, model, int(num_label_tokens))
 

@@ -40,6 +40,13 @@ def main(name, loss_kind, steps):
     if os.environ.get("B200_DROPIN_REPLICATE"):    # HSDP: distributed.dp_replicate_size
         y = y.replace("dp_size: none", "dp_size: none, dp_replicate_size: " + os.environ["B200_DROPIN_REPLICATE"])
         assert "dp_replicate_size" in y
+    if os.environ.get("B200_DROPIN_VAL"):          # a validation pass every step (the recipe's eval loop: model.eval(), is_train=False)
+        y = y.replace("max_steps: %d}" % c["steps"], "max_steps: %d, val_every_steps: 1}" % c["steps"])
+        y += (
+            "validation_dataset:\n  _target_: nemo_automodel.components.datasets.llm.mock_iterable_dataset.MockIterableDataset\n"
+            "  vocab_size: %d\n  seq_len: %d\n  num_samples: 3\n  batch_size: %d\n"
+            "validation_dataloader: {_target_: torch.utils.data.DataLoader, batch_size: null}\n" % (c["vocab"], c["seq"], c["lbs"]))
+        assert "val_every_steps" in y
     if loss_kind == "fused_loss":
         y = y.replace("_target_: nemo_automodel.components.loss.masked_ce.MaskedCrossEntropy", "_target_: automodel_b200.recipe.B200MaskedCrossEntropy")
     assert "b200_sharded" in y and "B200FusedAdamW" in y
@@ -84,6 +91,17 @@ def main(name, loss_kind, steps):
         return m
 
     r._run_train_optim_step = spy
+    if os.environ.get("B200_DROPIN_VAL"):
+        orig_val = r._run_validation_epoch
+
+        def val_spy(dl):
+            m = orig_val(dl)
+            rec.setdefault("val_loss", []).append(float(m.metrics["val_loss"]))
+            rec.setdefault("val_tokens", []).append(int(m.metrics["num_label_tokens"]))
+            rec.setdefault("training_flag_during_val", []).append(bool(model.training))
+            return m
+
+        r._run_validation_epoch = val_spy
     r.run_train_validation_loop()
     if os.environ.get("B200_DROPIN_DUMP"):   # per-rank record of what the reference's data loader fed (world-size > 1 check)
         import numpy as np

@@ -53,7 +53,10 @@ def _run_world(world, name, loss_kind, steps, **extra_env):
 
 @pytest.mark.parametrize("name,loss_kind,steps,loss_tol", [("hd128_fp32", "reference_loss", 2, 4e-3), ("tiny_bf16", "fused_loss", 8, 1e-3)])
 def test_reference_recipe_trains_through_b200_strategy(name, loss_kind, steps, loss_tol):
-    rec = _run(name, loss_kind, steps)
+    """Training curve vs the FSDP2 fixture; the fused-loss run also goes through the recipe's validation loop after every step
+    (model.eval(), is_train=False, loss_fn called with num_label_tokens=None = plain sum)."""
+    val = loss_kind == "fused_loss"
+    rec = _run(name, loss_kind, steps, **({"B200_DROPIN_VAL": "1"} if val else {}))
     _, meta = load(name)
     assert rec["model_class"] == "B200CausalLM" and rec["optimizer_class"] == "B200FusedAdamW"
     assert rec["loss_class"] == ("B200MaskedCrossEntropy" if loss_kind == "fused_loss" else "MaskedCrossEntropy")
@@ -65,6 +68,12 @@ def test_reference_recipe_trains_through_b200_strategy(name, loss_kind, steps, l
         assert rec["num_label_tokens"][s] == meta["num_label_tokens"][s]
         assert abs(rec["loss"][s] - meta["loss"][s]) < loss_tol, (s, rec["loss"][s], meta["loss"][s])
         assert abs(rec["grad_norm"][s] - meta["grad_norm"][s]) < 2e-2 * meta["grad_norm"][s], (s, rec["grad_norm"][s], meta["grad_norm"][s])
+    if val:
+        c = meta["config"]
+        assert rec["val_tokens"] == [3 * c["lbs"] * (c["seq"] - 1)] * n and not any(rec["training_flag_during_val"])
+        # random-init model on random tokens: the held-out loss sits at ln(vocab) like the training loss, resolved to better than 1e-3
+        assert all(abs(v - t) < 0.1 for v, t in zip(rec["val_loss"], rec["loss"])), (rec["val_loss"], rec["loss"])
+        assert len({round(v, 3) for v in rec["val_loss"]}) > 1, "validation loss is quantised (accumulator precision)"
 
 
 @pytest.mark.parametrize("gbs,sync_hook", [(4, True), (4, False)], ids=["ga2_sync_hook", "ga2_lazy_reduce_scatter"])
