@@ -178,6 +178,7 @@ class B200CausalLM(nn.Module):
         if not getattr(self, "_norm_ready", False):
             self.engine.compute_grad_norm_sq()
         self.engine.apply_adamw(getattr(self, "_max_norm", None), lr=lr)
+        self._max_norm = None          # a clip threshold applies to the step it was requested for (the benchmark recipe never clips)
         self._norm_ready = False
         self._first_micro = True
 

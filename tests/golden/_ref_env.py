@@ -10,9 +10,7 @@ REF = os.environ.get("B200_REFERENCE_PATH", "/root/reference")
 sys.path.insert(0, REF)
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-import numpy as np
-import transformers, transformers.utils.import_utils as iu
-from oracle.portable_init import portable_state_dict
+import transformers, transformers.utils.import_utils as iu  # noqa: F401
 
 iu.is_torchao_available()  # cache False before the stub exists
 
@@ -89,4 +87,19 @@ def _empty_like(t, *a, **k):
 
 
 torch.empty_like = _empty_like
+
+# the benchmark recipe's timers (components/training/timers.py:197, 361) synchronise and allocate on "the current CUDA device"
+torch.cuda.synchronize = lambda *a, **k: None
+torch.cuda.nvtx.range_push = lambda *a, **k: None
+torch.cuda.nvtx.range_pop = lambda *a, **k: None
+_zr = torch.zeros
+
+
+def _zeros(*a, **k):
+    if "device" in k:
+        k["device"] = _fix(k["device"])
+    return _zr(*a, **k)
+
+
+torch.zeros = _zeros
 

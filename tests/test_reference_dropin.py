@@ -166,3 +166,15 @@ def test_reference_checkpointer_world2_restores_sharded_optimizer_state(tmp_path
     for r in range(2):
         assert len(res[r]["loss"]) == 2
         assert res[r]["pre_state"][0] == full[r]["pre_state"][2], (r, res[r]["pre_state"][0], full[r]["pre_state"][2])
+
+
+def test_reference_benchmark_recipe_runs_over_the_b200_strategy():
+    """BenchmarkingRecipeForNextTokenPrediction (recipes/llm/benchmark.py: the reference's throughput harness - its own timers, no clip
+    utility, loss_fn called with num_label_tokens=None) over the facade with the fused loss: four iterations, four optimizer steps, and
+    the per-iteration loss it prints follows the FSDP2 fixture curve (Adam is invariant to the missing normalisation and clip)."""
+    rec = _run("tiny_bf16", "fused_loss", 4, B200_DROPIN_RECIPE="benchmark")
+    _, meta = load("tiny_bf16")
+    assert rec["model_class"] == "B200CausalLM" and rec["optimizer_class"] == "B200FusedAdamW" and rec["loss_class"] == "B200MaskedCrossEntropy"
+    assert rec["engine_steps"] == 4 and len(rec["loss"]) == 4
+    for s in range(4):
+        assert abs(rec["loss"][s] - meta["loss"][s]) < 2e-3, (s, rec["loss"][s], meta["loss"][s])     # printed with 4 decimals
