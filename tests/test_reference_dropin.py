@@ -6,6 +6,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 
 import pytest
 
@@ -20,7 +21,7 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "nemo_automo
 def _run(name, loss_kind, steps, **extra_env):
     env = dict(os.environ, PYTHONPATH=ROOT, TORCHDYNAMO_DISABLE="1", MASTER_ADDR="127.0.0.1", **extra_env)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "run_reference_recipe_b200.py"), name, loss_kind, str(steps)],
-                       capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+                       capture_output=True, text=True, timeout=900, env=env, cwd=tempfile.mkdtemp(prefix="b200_dropin_"))
     lines = [l for l in r.stdout.splitlines() if l.startswith("B200_DROPIN_RESULT ")]
     assert r.returncode == 0 and lines, (r.stdout[-2000:], r.stderr[-4000:])
     return json.loads(lines[-1][len("B200_DROPIN_RESULT "):])
@@ -37,11 +38,12 @@ def _run_world(world, name, loss_kind, steps, **extra_env):
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]
     procs = []
+    scratch = tempfile.mkdtemp(prefix="b200_dropin_")     # the recipe writes checkpoints/*.jsonl metric logs into its working directory
     for rank in range(world):
         env = dict(os.environ, PYTHONPATH=ROOT, TORCHDYNAMO_DISABLE="1", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
                    LOCAL_RANK=str(rank), WORLD_SIZE=str(world), **extra_env)
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "golden", "run_reference_recipe_b200.py"), name, loss_kind, str(steps)],
-                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT))
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=scratch))
     recs = []
     for p in procs:
         out, err = p.communicate(timeout=900)
