@@ -10,7 +10,7 @@ Inside a unit the HF parameters are laid out so that fused contractions see one 
 HF names/shapes (models/llama/model.py:85-101,162-166) are preserved as views for state_dict / checkpoint export.
 """
 from dataclasses import dataclass, field
-from typing import Dict, List, Tuple
+from typing import List, Tuple
 
 ALIGN = 8  # elements: 16-byte vector / TMA base alignment for bf16
 

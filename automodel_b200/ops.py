@@ -1,7 +1,6 @@
 """Tensor-level wrappers over the C ABI.  torch supplies device memory and streams only; every op below is one or
 more launches of the hand-written sm_100a kernels in csrc/.  Inputs must be CUDA bf16 (unless noted) and contiguous
 in the last dimension."""
-import math
 import torch
 
 from ._lib import lib, check

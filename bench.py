@@ -10,7 +10,6 @@ One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what each fie
 import argparse
 import contextlib
 import json
-import math
 import os
 import subprocess
 import sys

@@ -1,7 +1,6 @@
 """Multi-GPU parity of the sharded step (NCCL, world size 2): in-place reduce-scatter / all-gather on the flat buffers.
 Skipped on a single-GPU box; the same orchestration is covered on CPU over gloo in tests/test_engine_cpu.py."""
 import os
-import numpy as np
 import pytest
 import torch
 import torch.multiprocessing as mp

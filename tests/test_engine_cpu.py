@@ -2,7 +2,6 @@
 flat layout and fused-weight views, accumulate flags, grad-norm/clip/AdamW plumbing, and - over gloo, world size 2 - the
 in-place reduce-scatter / all-gather schedule.  Parity targets: the reference-generated fixtures and the numpy oracle."""
 import os
-import sys
 import numpy as np
 import pytest
 import torch

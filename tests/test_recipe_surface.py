@@ -3,7 +3,6 @@
 (loss * dp).backward() -> clip -> optimizer.step().  Runs on CPU with the stand-in kernels; parity target = the reference fixtures.
 When /root/reference is importable the reference's own MaskedCrossEntropy is the loss function."""
 import sys
-import numpy as np
 import pytest
 import torch
 
