@@ -509,11 +509,10 @@ class ShardedLlamaEngine:
             self._in_idx ^= 1
             nseq, max_len = self._fill_input_buffer(self._in_dev[k], input_ids, labels, position_ids)
             return (k, T, nseq, max_len)
-        if position_ids is None:
-            pos_np = np.tile(np.arange(S, dtype=np.int64), (b, 1))
-        else:
-            pos_np = position_ids.cpu().numpy()
-        cu_np, max_len = cu_seqlens_from_position_ids(pos_np)
+        # RoPE rotates by the index inside the row, as the reference's LlamaRotaryEmbedding does (it takes only the length from position_ids,
+        # rope_utils.py:212-235); position_ids only delimit the documents of a packed row (cu_seqlens for the varlen attention).
+        pos_np = np.tile(np.arange(S, dtype=np.int64), (b, 1))
+        cu_np, max_len = cu_seqlens_from_position_ids(pos_np if position_ids is None else position_ids.cpu().numpy())
         nseq = cu_np.size - 1
         k = self._in_idx
         self._in_idx ^= 1
@@ -547,13 +546,12 @@ class ShardedLlamaEngine:
             devb[T:2 * T].fill_(IGNORE_INDEX)
         else:
             devb[T:2 * T].copy_(labels.reshape(-1))
+        devb[2 * T:3 * T].view(b, S).copy_(torch.arange(S, dtype=torch.int32, device=dev))     # RoPE positions = index inside the row
         if position_ids is None:
-            devb[2 * T:3 * T].view(b, S).copy_(torch.arange(S, dtype=torch.int32, device=dev))
             devb[3 * T:3 * T + b + 1].copy_(torch.arange(0, T + 1, S, dtype=torch.int32, device=dev))
             return b, S
         cu_np, max_len = cu_seqlens_from_position_ids(position_ids.cpu().numpy())
         nseq = cu_np.size - 1
-        devb[2 * T:3 * T].copy_(position_ids.reshape(-1))
         devb[3 * T:3 * T + nseq + 1].copy_(torch.from_numpy(cu_np).to(dev, non_blocking=True))
         return nseq, max_len
 

@@ -218,9 +218,14 @@ def forward_backward(params, cfg, input_ids, labels, num_label_tokens, prec="fp3
     W = {k: np.asarray(v, dtype=P.dt) for k, v in params.items()}
     if position_ids is None:
         position_ids = np.broadcast_to(np.arange(S), (b, S))
-    cos_t, sin_t = rope_tables(cfg, int(position_ids.max()) + 1, P)
-    cos = cos_t[position_ids][:, None]  # [b,1,S,d]
-    sin = sin_t[position_ids][:, None]
+    # The reference's LlamaRotaryEmbedding takes only the LENGTH from position_ids and returns the tables of positions [0, S)
+    # (components/models/llama/rope_utils.py:212-235): a packed row is rotated by its row index, not by the restarting position_ids.
+    # Within a document this is the same rotation up to the rounding of the table entries (RoPE is relative); position_ids only
+    # delimit the documents (HF flash-attention derives cu_seqlens from them).
+    row_pos = np.broadcast_to(np.arange(S), (b, S))
+    cos_t, sin_t = rope_tables(cfg, S, P)
+    cos = cos_t[row_pos][:, None]  # [b,1,S,d]
+    sin = sin_t[row_pos][:, None]
     packed = bool((position_ids[:, 1:] <= position_ids[:, :-1]).any())
     seg = segments_from_position_ids(position_ids) if packed else None
 
