@@ -35,6 +35,11 @@ class B200ShardedConfig:
     reference_rounding: bool = True  # bf16(bf16(acc) + residual), as the reference's two eager ops
     max_positions: Optional[int] = None
     activation_checkpointing: bool = False   # same key as FSDP2Config.activation_checkpointing (distributed/config.py:49-136)
+    # Packed rows (several documents per row, position_ids restarting at each): True = always derive the documents from position_ids (one
+    # device->host read per micro-batch when the batch already lives on the GPU), False = never, None = auto (CPU position_ids are
+    # inspected for free; CUDA position_ids are inspected for the first micro-batches and afterwards only checked asynchronously, so a
+    # plain SFT run keeps the host running ahead of the GPU and a packed batch that appears later still fails loudly one step later).
+    packed_sequences: Optional[bool] = None
     backend: str = "nccl"                    # accepted for YAML compatibility (`distributed.backend`); torch.distributed is set up by the recipe
 
 
@@ -103,6 +108,10 @@ class B200CausalLM(nn.Module):
         self._first_micro = True
         self._last_handle = None
         self._last_shape = None
+        self.packed_sequences = None          # see B200ShardedConfig.packed_sequences (set by B200ShardedManager.parallelize)
+        self._pack_probes_left = 3
+        self._pack_flag = None                 # device bool: "a CUDA batch skipped by the auto mode had restarting position_ids"
+        self._pack_check = None                # (pinned host copy, event) of the flag taken at the previous optimizer step
         engine._facade = weakref.ref(self)   # lets the optimizer built from `model.parameters()` find the module that owns the step state
         self._anchor = nn.Parameter(torch.zeros((), device=engine.device), requires_grad=True)  # keeps the autograd node alive
         # HF-named parameters as views of the flat buffers; .grad = views of the flat gradient buffers.  They hang on a skeleton of empty
@@ -160,11 +169,43 @@ class B200CausalLM(nn.Module):
         if logits_to_keep not in (None, 0):
             raise NotImplementedError("B200CausalLM computes logits for all positions (logits_to_keep must be None or 0)")
         eng = self.engine
-        handle = eng.stage(input_ids, labels, position_ids)   # labels=None: the recipe hands them to the loss function (set_labels)
+        handle = eng.stage(input_ids, labels, self._document_position_ids(position_ids))   # labels=None: the loss function gets them (set_labels)
         self._last_handle, self._last_shape = handle, tuple(input_ids.shape)
         logits = _Fwd.apply(self._anchor, self, handle, input_ids.shape[0], input_ids.shape[1])
         logits._b200_model = self
         return SimpleNamespace(logits=logits)
+
+    def _document_position_ids(self, position_ids):
+        """position_ids only matter as document delimiters of packed rows (RoPE rotates by the index inside the row, like the reference's
+        rotary module).  Returns them when they must be inspected, None when the batch is to be treated as one document per row."""
+        if position_ids is None or self.packed_sequences is False:
+            return None
+        if self.packed_sequences is True or position_ids.device.type == "cpu":
+            return position_ids
+        if self._pack_probes_left > 0:        # auto mode, CUDA tensors: look (with a sync) at the first few micro-batches
+            self._pack_probes_left -= 1
+            if bool((position_ids[:, 1:] <= position_ids[:, :-1]).any()):
+                self.packed_sequences = True
+            return position_ids
+        flag = (position_ids[:, 1:] <= position_ids[:, :-1]).any().reshape(1)
+        self._pack_flag = flag if self._pack_flag is None else (self._pack_flag | flag)
+        return None
+
+    def _poll_pack_check(self):
+        """Auto mode: the asynchronous verdict on the batches that were NOT inspected (no sync: the copy was issued one step ago)."""
+        if self._pack_check is not None:
+            host, ev = self._pack_check
+            if ev.query():
+                self._pack_check = None
+                if bool(host[0]):
+                    raise RuntimeError("a packed batch (position_ids restarting inside a row) arrived after the first micro-batches; set "
+                                       "distributed.packed_sequences: true so documents are always derived from position_ids")
+        if self._pack_flag is not None and self._pack_check is None:
+            host = torch.empty(1, dtype=torch.bool, pin_memory=True)
+            host.copy_(self._pack_flag, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._pack_check, self._pack_flag = (host, ev), None
 
     # ---- hooks for the clip utility / optimizer
     def b200_clip_grad_norm(self, max_norm: Optional[float]):
@@ -177,6 +218,7 @@ class B200CausalLM(nn.Module):
     def b200_optimizer_step(self, lr=None):
         if not getattr(self, "_norm_ready", False):
             self.engine.compute_grad_norm_sq()
+        self._poll_pack_check()
         self.engine.apply_adamw(getattr(self, "_max_norm", None), lr=lr)
         self._max_norm = None          # a clip threshold applies to the step it was requested for (the benchmark recipe never clips)
         self._norm_ready = False
@@ -294,4 +336,6 @@ class B200ShardedManager:
             sd = {k: v for k, v in model.state_dict().items()}
             if all(getattr(v, "device", torch.device("cpu")).type != "meta" for v in sd.values()):
                 eng.load_state_dict(sd)
-        return B200CausalLM(cfg, eng)
+        model = B200CausalLM(cfg, eng)
+        model.packed_sequences = self.config.packed_sequences
+        return model

@@ -89,3 +89,29 @@ def _run_recipe_loop(loss_kind, device, ops):
     p = dict(model.named_parameters())["lm_head.weight"]
     assert p.data_ptr() == model.engine.P["lm_head.weight"].data_ptr()
     assert p.grad.data_ptr() == model.engine.G["lm_head.weight"].data_ptr()
+
+
+def test_position_ids_are_document_delimiters_only():
+    """B200ShardedConfig.packed_sequences: position_ids reach the engine only as document delimiters (None = one document per row)."""
+    z, meta = load("hd128_fp32")
+    cfg = model_cfg(meta)
+    S = meta["config"]["seq"]
+    plain = torch.arange(S)[None]
+    packed = torch.cat([torch.arange(100), torch.arange(S - 100)])[None]
+    for mode, want_plain, want_packed in ((None, True, True), (True, True, True), (False, False, False)):
+        mgr = B200ShardedManager(B200ShardedConfig(max_tokens=S, packed_sequences=mode), device=torch.device("cpu"), ops=cpu_kernels)
+        model = mgr.parallelize(_Cfg(cfg))
+        assert (model._document_position_ids(plain) is not None) == want_plain
+        assert (model._document_position_ids(packed) is not None) == want_packed
+        assert model._document_position_ids(None) is None
+    # and they change the result exactly when they delimit documents
+    mgr = B200ShardedManager(B200ShardedConfig(max_tokens=S), device=torch.device("cpu"), ops=cpu_kernels)
+    model = mgr.parallelize(_Cfg(cfg))
+    model.engine.load_state_dict(init_params(meta))
+    ids = torch.from_numpy(batches(z, meta, 0)[0]["input_ids"])
+    with torch.no_grad():
+        a = model(input_ids=ids).logits.float().clone()
+        b = model(input_ids=ids, position_ids=plain).logits.float().clone()
+        c = model(input_ids=ids, position_ids=packed).logits.float().clone()
+    assert torch.equal(a, b)
+    assert torch.equal(a[:, :100], c[:, :100]) and not torch.equal(a[:, 100:], c[:, 100:])
