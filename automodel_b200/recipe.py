@@ -65,8 +65,14 @@ class _Fwd(torch.autograd.Function):
         scale = 1.0 / (eng.world * eng.replicas)
         if d2.data_ptr() != buf.data_ptr():
             buf.copy_(d2 if scale == 1.0 else d2 * scale)
-        elif scale != 1.0:
-            buf.mul_(scale)
+        else:
+            # fused loss: the buffer already holds dlogits for a unit upstream gradient; fold the upstream scalar (a DEVICE tensor: reading
+            # it on the host would stall the launch queue once per micro-batch) and 1/dp in with one in-place multiply
+            up = model._upstream_grad
+            model._upstream_grad = None
+            t = scale if up is None else up.to(torch.float32) * scale
+            if up is not None or scale != 1.0:
+                buf.mul_(t)
         eng.backward_from_dlogits(ctx.handle, first_micro=model._first_micro, last_micro=bool(model._sync_grads))
         model._first_micro = False
         return None, None, None, None, None
@@ -83,14 +89,11 @@ class _FusedLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        # dlogits are already in the engine buffer (scaled by 1/num_label_tokens); fold the upstream scalar in
-        eng = ctx.model.engine
-        T = ctx.model._last_handle[1]
-        gv = float(g) if g.numel() == 1 else None
-        out = eng.logits[:T].view(ctx.model._last_shape[0], ctx.model._last_shape[1], -1)
-        if gv is not None and gv != 1.0:
-            out = out * gv
-        return out, None, None
+        # dlogits are already in the engine buffer (scaled by 1/num_label_tokens); the upstream scalar is applied by _Fwd.backward
+        model = ctx.model
+        model._upstream_grad = g.reshape(()) if g.numel() == 1 else None
+        T = model._last_handle[1]
+        return model.engine.logits[:T].view(model._last_shape[0], model._last_shape[1], -1), None, None
 
 
 class _Node(nn.Module):
@@ -108,6 +111,7 @@ class B200CausalLM(nn.Module):
         self._first_micro = True
         self._last_handle = None
         self._last_shape = None
+        self._upstream_grad = None
         self.packed_sequences = None          # see B200ShardedConfig.packed_sequences (set by B200ShardedManager.parallelize)
         self._pack_probes_left = 3
         self._pack_flag = None                 # device bool: "a CUDA batch skipped by the auto mode had restarting position_ids"
