@@ -60,6 +60,13 @@ def main(name, loss_kind, steps):
     with tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False) as f:
         f.write(y)
         path = f.name
+    pre = os.environ.get("B200_DROPIN_PRETRAINED")      # model section = NeMoAutoModelForCausalLM.from_pretrained(<local HF checkpoint dir>)
+    if pre:
+        i, j = y.index("model:\n"), y.index("checkpoint:")
+        y = (y[:i] + "model:\n  _target_: nemo_automodel.NeMoAutoModelForCausalLM.from_pretrained\n  pretrained_model_name_or_path: %s\n"
+             "  torch_dtype: bfloat16\n  attn_implementation: sdpa\n  use_liger_kernel: false\n" % pre + y[j:])
+        with open(path, "w") as f:
+            f.write(y)
     bench = os.environ.get("B200_DROPIN_RECIPE") == "benchmark"     # the reference's BenchmarkingRecipeForNextTokenPrediction instead
     if bench:
         with open(path, "a") as f:
@@ -73,6 +80,17 @@ def main(name, loss_kind, steps):
     r.setup()
     model = r.model_parts[0]
     z, meta = load(name)
+    if pre:
+        from safetensors.torch import load_file
+        want = {}
+        for fn in sorted(os.listdir(pre)):
+            if fn.endswith(".safetensors"):
+                want.update(load_file(os.path.join(pre, fn)))
+        got = model.state_dict()
+        mism = [k for k in want if k not in got or not torch.equal(got[k].cpu(), want[k])]
+        sys.stdout.write("\nB200_DROPIN_RESULT " + json.dumps({"pretrained_tensors": len(want), "pretrained_mismatch": mism,
+                                                               "model_class": type(model).__name__}) + "\n")
+        return
     if not (ck and restore):
         model.engine.load_state_dict(init_params(meta))     # the snapshot the fixture run started from
     rec = {"loss": [], "grad_norm": [], "num_label_tokens": [], "ids_match": [], "pre_state": []}

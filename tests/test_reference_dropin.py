@@ -180,3 +180,20 @@ def test_reference_benchmark_recipe_runs_over_the_b200_strategy():
     assert rec["engine_steps"] == 4 and len(rec["loss"]) == 4
     for s in range(4):
         assert abs(rec["loss"][s] - meta["loss"][s]) < 2e-3, (s, rec["loss"][s], meta["loss"][s])     # printed with 4 decimals
+
+
+def test_from_pretrained_through_the_reference_loader(tmp_path):
+    """SURVEY §8f N1, load direction: `NeMoAutoModelForCausalLM.from_pretrained(<HF checkpoint>)` + `strategy: b200_sharded` -
+    every tensor of the checkpoint arrives bit-exactly in the flat unit buffers (HF names are views of them)."""
+    import torch
+    import transformers
+    _, meta = load("hd128_fp32")
+    c = meta["config"]
+    cfg = transformers.LlamaConfig(vocab_size=c["vocab"], hidden_size=c["hidden"], intermediate_size=c["ffn"], num_hidden_layers=c["layers"],
+                                   num_attention_heads=c["heads"], num_key_value_heads=c["kv"], max_position_embeddings=c["seq"],
+                                   rms_norm_eps=1e-5, rope_theta=c["theta"], tie_word_embeddings=False)
+    torch.manual_seed(3)
+    transformers.LlamaForCausalLM(cfg).to(torch.bfloat16).save_pretrained(str(tmp_path / "hf"))
+    rec = _run("hd128_fp32", "reference_loss", 1, B200_DROPIN_PRETRAINED=str(tmp_path / "hf"))
+    assert rec["model_class"] == "B200CausalLM" and rec["pretrained_tensors"] == 2 + 9 * c["layers"] + 1
+    assert rec["pretrained_mismatch"] == []
