@@ -163,6 +163,21 @@ class B200CausalLM(nn.Module):
         self.engine.refresh_master_()
         return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
+    def initialize_weights(self):
+        """Random initialisation AFTER sharding: what `Checkpointer.initialize_model_weights` calls on the parallelized model when the
+        recipe built it on the meta device (from_config, and from_pretrained before the checkpoint overwrites it;
+        components/checkpoint/checkpointing.py:574-676, _transformers/infrastructure.py:528-552).  HF `_init_weights` semantics: N(0,
+        config.initializer_range) for projections and embeddings, ones for the norms.  Every data-parallel rank must end with the same
+        parameters, so the seed is the global rank 0's torch seed."""
+        import torch.distributed as dist
+        seed = torch.tensor([torch.initial_seed() % (2 ** 31)], dtype=torch.int64)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            seed = seed.to(self.engine.device if dist.get_backend() == "nccl" else "cpu")
+            dist.broadcast(seed, src=0)
+        cfg = self.config
+        std = (cfg.get("initializer_range", 0.02) if isinstance(cfg, dict) else getattr(cfg, "initializer_range", 0.02)) or 0.02
+        self.engine.init_random_(seed=int(seed.item()), std=float(std))
+
     def set_requires_gradient_sync(self, flag: bool, recurse: bool = True):
         """FSDPModule API used by get_sync_ctx: False on all but the last micro-batch (defer_fsdp_grad_sync)."""
         self._sync_grads = bool(flag)

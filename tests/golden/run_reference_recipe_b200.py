@@ -80,6 +80,9 @@ def main(name, loss_kind, steps):
     r.setup()
     model = r.model_parts[0]
     z, meta = load(name)
+    # what the recipe's own initialisation left in the flat buffers (from_config: Checkpointer.initialize_model_weights, before or after
+    # sharding depending on the world size)
+    init_fp = [float(sum(p.double().abs().sum() for p in model.engine.p_full)), float(min(float(p.float().abs().max()) for p in model.engine.P.values()))]
     if pre:
         from safetensors.torch import load_file
         want = {}
@@ -93,7 +96,7 @@ def main(name, loss_kind, steps):
         return
     if not (ck and restore):
         model.engine.load_state_dict(init_params(meta))     # the snapshot the fixture run started from
-    rec = {"loss": [], "grad_norm": [], "num_label_tokens": [], "ids_match": [], "pre_state": []}
+    rec = {"loss": [], "grad_norm": [], "num_label_tokens": [], "ids_match": [], "pre_state": [], "recipe_init": init_fp}
     dump = {}
     step_i = [0]
     orig = r._run_train_optim_step

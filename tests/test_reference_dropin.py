@@ -62,6 +62,7 @@ def test_reference_recipe_trains_through_b200_strategy(name, loss_kind, steps, l
     _, meta = load(name)
     assert rec["model_class"] == "B200CausalLM" and rec["optimizer_class"] == "B200FusedAdamW"
     assert rec["loss_class"] == ("B200MaskedCrossEntropy" if loss_kind == "fused_loss" else "MaskedCrossEntropy")
+    assert rec["recipe_init"][0] > 0 and rec["recipe_init"][1] > 0, "the recipe's own (meta-device -> initialize_weights) init left zero tensors"
     assert all(rec["ids_match"]), "the reference data loader fed different batches than in the fixture run"
     assert rec["max_grad_norm"] == meta["max_grad_norm"]
     n = len(rec["loss"])
@@ -89,6 +90,9 @@ def test_reference_recipe_world2_equals_single_rank_accumulation(tmp_path, gbs, 
                        B200_DROPIN_NO_SYNC_HOOK="0" if sync_hook else "1")
     assert recs[0]["loss"] == recs[1]["loss"] and recs[0]["grad_norm"] == recs[1]["grad_norm"]
     assert recs[0]["num_micro"] == [gbs // 2] * len(recs[0]["loss"])
+    # the recipe's own initialisation (meta device -> parallelize -> Checkpointer.initialize_model_weights -> facade.initialize_weights):
+    # non-zero and identical on both ranks
+    assert recs[0]["recipe_init"] == recs[1]["recipe_init"] and recs[0]["recipe_init"][0] > 0 and recs[0]["recipe_init"][1] > 0
     _replay_and_compare(tmp_path, recs, 2)
 
 
