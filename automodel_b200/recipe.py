@@ -347,14 +347,28 @@ class B200ShardedManager:
         cfg = model.config if hasattr(model, "config") else model
         dev = self.device if self.device is not None else torch.device("cuda", torch.cuda.current_device())
         od = optimizer_defaults or {}
-        eng = ShardedLlamaEngine(cfg.to_dict() if hasattr(cfg, "to_dict") else cfg, dev, process_group=self.pg, max_tokens=self.config.max_tokens,
+        cfg_d = cfg.to_dict() if hasattr(cfg, "to_dict") else cfg
+        if hasattr(model, "named_parameters"):
+            # the engine trains exactly the HF Llama parameter set, all of it: anything else must fail here (before any device memory is
+            # taken), not train something different
+            from .layout import LlamaDims, build_layout
+            expected = {sl.name for u in build_layout(LlamaDims.from_hf(cfg_d), 1) for sl in u.slots}
+            names = {n for n, _ in model.named_parameters()}
+            extra, missing = sorted(names - expected), sorted(expected - names)
+            if extra or missing:
+                raise NotImplementedError(f"strategy b200_sharded: the model's parameters are not the Llama set the engine implements "
+                                          f"(unexpected {extra[:3]}, missing {missing[:3]}); PEFT adapters / other architectures are not supported")
+            frozen = [n for n, p in model.named_parameters() if not p.requires_grad]
+            if frozen:
+                raise NotImplementedError(f"strategy b200_sharded trains every parameter; frozen parameters are not supported ({frozen[:3]})")
+        eng = ShardedLlamaEngine(cfg_d, dev, process_group=self.pg, max_tokens=self.config.max_tokens,
                                  adam_mode=self.config.adam_mode, master_weights=self.config.master_weights,
                                  reference_rounding=self.config.reference_rounding, max_positions=self.config.max_positions,
                                  activation_checkpointing=self.config.activation_checkpointing, replica_group=self.rpg, ops=self.ops, **od)
-        if hasattr(model, "state_dict") and any(True for _ in model.state_dict()):
-            sd = {k: v for k, v in model.state_dict().items()}
-            if all(getattr(v, "device", torch.device("cpu")).type != "meta" for v in sd.values()):
-                eng.load_state_dict(sd)
+        if hasattr(model, "named_parameters"):
+            sd = model.state_dict()
+            if sd and all(getattr(v, "device", torch.device("cpu")).type != "meta" for v in sd.values()):
+                eng.load_state_dict(sd)      # materialised model (single-GPU load-before-shard); a meta model is initialised / loaded afterwards
         model = B200CausalLM(cfg, eng)
         model.packed_sequences = self.config.packed_sequences
         return model

@@ -115,3 +115,27 @@ def test_position_ids_are_document_delimiters_only():
         c = model(input_ids=ids, position_ids=packed).logits.float().clone()
     assert torch.equal(a, b)
     assert torch.equal(a[:, :100], c[:, :100]) and not torch.equal(a[:, 100:], c[:, 100:])
+
+
+def test_parallelize_rejects_models_it_would_not_train_faithfully():
+    """PEFT adapters (extra parameters) and frozen parameters must fail at parallelize time, before any memory is taken."""
+    import transformers
+    z, meta = load("hd128_fp32")
+    c = meta["config"]
+    hf_cfg = transformers.LlamaConfig(vocab_size=c["vocab"], hidden_size=c["hidden"], intermediate_size=c["ffn"], num_hidden_layers=c["layers"],
+                                      num_attention_heads=c["heads"], num_key_value_heads=c["kv"], max_position_embeddings=c["seq"],
+                                      rope_theta=c["theta"], tie_word_embeddings=False)
+    mgr = B200ShardedManager(B200ShardedConfig(max_tokens=c["seq"]), device=torch.device("cpu"), ops=cpu_kernels)
+    with torch.device("meta"):
+        ok = transformers.LlamaForCausalLM(hf_cfg)
+    assert isinstance(mgr.parallelize(ok), B200CausalLM)            # a meta model of the right family is accepted (initialised later)
+    with torch.device("meta"):
+        lora = transformers.LlamaForCausalLM(hf_cfg)
+    lora.model.layers[0].self_attn.q_proj.lora_A = torch.nn.Parameter(torch.empty(8, c["hidden"], device="meta"))
+    with pytest.raises(NotImplementedError, match="PEFT"):
+        mgr.parallelize(lora)
+    with torch.device("meta"):
+        frozen = transformers.LlamaForCausalLM(hf_cfg)
+    frozen.model.embed_tokens.weight.requires_grad_(False)
+    with pytest.raises(NotImplementedError, match="frozen"):
+        mgr.parallelize(frozen)
