@@ -188,6 +188,11 @@ class B200CausalLM(nn.Module):
         if logits_to_keep not in (None, 0):
             raise NotImplementedError("B200CausalLM computes logits for all positions (logits_to_keep must be None or 0)")
         eng = self.engine
+        if getattr(self, "_norm_ready", False) and self.training:
+            # the clip utility ran but B200FusedAdamW.step() did not: another optimizer is stepping the parameter views.  That would skip
+            # the clip (it is applied inside the fused AdamW) and, with more than one rank, update from reduce-scattered gradient buffers
+            raise RuntimeError("B200CausalLM must be optimised by automodel_b200.recipe.B200FusedAdamW "
+                               "(optimizer: {_target_: automodel_b200.recipe.B200FusedAdamW, ...}); another optimizer stepped it")
         handle = eng.stage(input_ids, labels, self._document_position_ids(position_ids))   # labels=None: the loss function gets them (set_labels)
         self._last_handle, self._last_shape = handle, tuple(input_ids.shape)
         logits = _Fwd.apply(self._anchor, self, handle, input_ids.shape[0], input_ids.shape[1])

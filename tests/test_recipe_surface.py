@@ -139,3 +139,22 @@ def test_parallelize_rejects_models_it_would_not_train_faithfully():
     frozen.model.embed_tokens.weight.requires_grad_(False)
     with pytest.raises(NotImplementedError, match="frozen"):
         mgr.parallelize(frozen)
+
+
+def test_foreign_optimizer_is_detected():
+    """torch.optim.AdamW on the facade's parameter views would skip the clip and, sharded, read reduce-scattered buffers: the next
+    training forward after a clip that was not followed by B200FusedAdamW.step() fails loudly."""
+    z, meta = load("hd128_fp32")
+    mgr = B200ShardedManager(B200ShardedConfig(max_tokens=meta["config"]["seq"]), device=torch.device("cpu"), ops=cpu_kernels)
+    model = mgr.parallelize(_Cfg(model_cfg(meta)))
+    model.engine.load_state_dict(init_params(meta))
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    b = batches(z, meta, 0)[0]
+    ids, lab = torch.from_numpy(b["input_ids"]), torch.from_numpy(b["labels"])
+    out = model(input_ids=ids)
+    loss = _TorchMaskedCE()(logits=out.logits, labels=lab, num_label_tokens=int((lab != -100).sum()))
+    loss.backward()
+    model.b200_clip_grad_norm(1.0)
+    opt.step()
+    with pytest.raises(RuntimeError, match="B200FusedAdamW"):
+        model(input_ids=ids)
