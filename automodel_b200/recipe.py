@@ -273,9 +273,9 @@ class B200MaskedCrossEntropy(nn.Module):
 class B200FusedAdamW(torch.optim.Optimizer):
     """optimizer `_target_`: fused AdamW on the flat shards of the engine that owns `params`."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1, amsgrad=False, maximize=False, foreach=None,
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=False, maximize=False, foreach=None,
                  fused=None, capturable=False, differentiable=False):
-        # torch.optim.AdamW's keyword set, so a YAML written for it only needs the `_target_` changed: implementation hints (foreach,
+        # torch.optim.AdamW's keyword set AND defaults, so a YAML written for it only needs the `_target_` changed: implementation hints (foreach,
         # fused, capturable) mean nothing here, options that change the mathematics are refused
         if amsgrad or maximize or differentiable:
             raise NotImplementedError("B200FusedAdamW implements plain AdamW (amsgrad / maximize / differentiable are not supported)")
