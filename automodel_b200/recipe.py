@@ -41,6 +41,30 @@ class B200ShardedConfig:
     # plain SFT run keeps the host running ahead of the GPU and a packed batch that appears later still fails loudly one step later).
     packed_sequences: Optional[bool] = None
     backend: str = "nccl"                    # accepted for YAML compatibility (`distributed.backend`); torch.distributed is set up by the recipe
+    # --- FSDP2Config's remaining keys (components/distributed/config.py:106-120), so that an FSDP2 YAML only needs `strategy:` changed.
+    # Scheduling hints are accepted and ignored (this engine has its own overlap schedule); options that would change what is computed
+    # are refused in __post_init__.
+    defer_fsdp_grad_sync: bool = True        # gradients always accumulate unsharded and are reduce-scattered once per optimizer step
+    enable_fsdp2_prefetch: bool = False
+    fsdp2_backward_prefetch_depth: int = 2
+    fsdp2_forward_prefetch_depth: int = 1
+    enable_compile: bool = False
+    patch_is_packed_sequence: bool = False
+    mp_policy: Optional[object] = None       # only bf16 parameters / compute (the reduce-scatter runs in bf16 with fp32 accumulation per pair)
+    sequence_parallel: bool = False
+    tp_plan: Optional[dict] = None
+    offload_policy: Optional[object] = None
+    autocast_dtype: Optional[object] = None
+    enable_async_tensor_parallel: bool = False
+
+    def __post_init__(self):
+        bad = [k for k in ("sequence_parallel", "enable_async_tensor_parallel", "enable_compile") if getattr(self, k)]
+        bad += [k for k in ("tp_plan", "offload_policy", "autocast_dtype") if getattr(self, k) is not None]
+        if bad:
+            raise ValueError(f"strategy b200_sharded does not support {bad} (data-parallel bf16 training without offload / compile)")
+        pd = getattr(self.mp_policy, "param_dtype", None)
+        if pd is not None and pd != torch.bfloat16:
+            raise ValueError(f"strategy b200_sharded computes in bf16; mp_policy.param_dtype={pd} is not supported")
 
 
 class _Fwd(torch.autograd.Function):

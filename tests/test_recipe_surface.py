@@ -158,3 +158,24 @@ def test_foreign_optimizer_is_detected():
     opt.step()
     with pytest.raises(RuntimeError, match="B200FusedAdamW"):
         model(input_ids=ids)
+
+
+def test_strategy_config_accepts_an_fsdp2_yaml_and_refuses_what_it_cannot_honour():
+    """Every FSDP2Config key is a B200ShardedConfig key (so `_validate_strategy_kwargs`, recipes/_dist_setup.py:44-54, lets an FSDP2 YAML
+    through with only `strategy:` changed); keys that would change the computation raise."""
+    import dataclasses
+    try:
+        sys.path.insert(0, "/root/reference")
+        from nemo_automodel.components.distributed.config import FSDP2Config
+        theirs = {f.name for f in dataclasses.fields(FSDP2Config)}
+    except Exception:
+        theirs = {"sequence_parallel", "tp_plan", "mp_policy", "offload_policy", "activation_checkpointing", "defer_fsdp_grad_sync", "backend"}
+    finally:
+        if sys.path[0] == "/root/reference":
+            sys.path.pop(0)
+    ours = {f.name for f in dataclasses.fields(B200ShardedConfig)}
+    assert theirs <= ours, sorted(theirs - ours)
+    B200ShardedConfig(defer_fsdp_grad_sync=False, enable_fsdp2_prefetch=True, fsdp2_backward_prefetch_depth=1, backend="gloo")
+    for bad in (dict(sequence_parallel=True), dict(enable_compile=True), dict(tp_plan={"a": 1}), dict(offload_policy=object())):
+        with pytest.raises(ValueError):
+            B200ShardedConfig(**bad)
