@@ -2,6 +2,7 @@
 # First GPU call of the next round (one GPU, ~3 min): everything written after the round-1 GPU budget ran out.
 #   gpurun --timeout 600 -- bash tools/r2_first_run.sh
 mkdir -p gpurun_out
+timeout 400 python -m pytest tests -q -m gpu > gpurun_out/r2_gpu_suite.log 2>&1; echo "default gpu suite rc=$?"; tail -3 gpurun_out/r2_gpu_suite.log
 B200_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_experimental_gpu.py -q -m gpu > gpurun_out/r2_experimental.log 2>&1; echo "experimental rc=$?"; tail -3 gpurun_out/r2_experimental.log
 for cfg in "0 engine" "1 engine" "0 facade" "0 engine-swiglu"; do
   set -- $cfg
