@@ -39,6 +39,10 @@ class LlamaDims:
             raise ValueError(f"model_type {mt!r}: the B200 sharded step implements the Llama decoder (llama, and mistral without sliding window)")
         if g("sliding_window"):
             raise ValueError("sliding-window attention is not supported")
+        if g("hidden_act", "silu") not in (None, "silu"):
+            raise ValueError(f"hidden_act {g('hidden_act')!r}: the MLP kernels implement SwiGLU (silu) only")
+        if (g("attention_dropout", 0.0) or 0.0) != 0.0:
+            raise ValueError("attention_dropout != 0 is not supported")
         if g("tie_word_embeddings", False):
             raise ValueError("tie_word_embeddings=True is not supported by the B200 flat layout (Llama-3 is untied)")
         if g("attention_bias", False) or g("mlp_bias", False):

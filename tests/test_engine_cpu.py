@@ -265,7 +265,8 @@ def test_unsupported_configs_are_rejected_loudly():
     base = dict(vocab_size=512, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=1,
                 max_position_embeddings=256, rms_norm_eps=1e-5)
     from automodel_b200.engine import _rope_inv_freq
-    for bad in (dict(model_type="qwen2"), dict(sliding_window=4096), dict(tie_word_embeddings=True), dict(attention_bias=True), dict(mlp_bias=True)):
+    for bad in (dict(model_type="qwen2"), dict(sliding_window=4096), dict(tie_word_embeddings=True), dict(attention_bias=True), dict(mlp_bias=True),
+                dict(hidden_act="gelu"), dict(attention_dropout=0.1)):
         with pytest.raises(ValueError):
             LlamaDims.from_hf(dict(base, **bad))
     with pytest.raises(ValueError):
