@@ -38,12 +38,12 @@ def _worker(rank, world, port, out_q, peer_comm="1"):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 _MODES = [("1", "nvlink_peer_path"), ("0", "nccl_collectives")]
 if os.environ.get("B200_TEST_EXPERIMENTAL") == "1":     # written after the last multi-GPU run of round 1: opt-in until it has passed once
     _MODES.append(("ag", "nccl_rs_copy_engine_ag"))
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("peer_comm", [m for m, _ in _MODES], ids=[i for _, i in _MODES])
 def test_world2_matches_reference_curve(peer_comm):
     ctx = mp.get_context("spawn")
