@@ -143,6 +143,7 @@ class ShardedLlamaEngine:
         # Default: on for one GPU (measured +2.3..3.4 %); with N > 1 it is opt-in until it has been measured next to the NCCL kernels.
         self._wg_on = self.streams.cuda and os.environ.get("B200_WGRAD_STREAM", "1" if self.world == 1 else "0") == "1"
         self.opt_overlap = self.streams.cuda and os.environ.get("B200_OPT_OVERLAP", "1") != "0"   # optimizer sweep on its own stream
+        self._overlap_cfg = (self._wg_on, self.opt_overlap)     # what set_stream_overlap(True) restores
         self._wg_pending = {}     # tmp buffer name -> event of the last side-stream GEMM that reads it (WAR guard for the next writer)
         self._wg_last = None
         # B200_FUSE_SWIGLU=1: SwiGLU computed in the epilogue of the gate/up GEMM (b200_gemm_bf16 flag 4) instead of a separate HBM pass
@@ -482,12 +483,12 @@ class ShardedLlamaEngine:
 
     def set_stream_overlap(self, on: bool):
         """Measurement aid: with overlap off every kernel of the step runs back to back on the compute stream (weight-gradient GEMMs and
-        the optimizer sweep included), so per-kernel CUDA-event durations are the kernels' own.  Results are identical either way."""
+        the optimizer sweep included), so per-kernel CUDA-event durations are the kernels' own; on = back to the schedule this engine was
+        configured with (B200_WGRAD_STREAM / B200_OPT_OVERLAP and their world-size defaults).  Results are identical either way."""
         self.sync_params()
         if self.streams.cuda:
             torch.cuda.synchronize(self.device)
-        self._wg_on = bool(on) and self.streams.cuda
-        self.opt_overlap = bool(on) and self.streams.cuda
+        self._wg_on, self.opt_overlap = self._overlap_cfg if on else (False, False)   # on = the configured schedule, not "everything"
 
     def sync_params(self):
         """Make the current stream wait for every pending parameter update (state_dict readers, checkpointing)."""
