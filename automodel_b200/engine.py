@@ -55,11 +55,13 @@ def _rope_inv_freq(d: LlamaDims) -> torch.Tensor:
 
 def rope_tables(d: LlamaDims, n_pos: int, device) -> (torch.Tensor, torch.Tensor):
     """bf16 cos/sin tables [n_pos, head_dim] (rope_utils.py:191-205: fp32 math, rounded to the model dtype)."""
-    inv = _rope_inv_freq(d)
-    t = torch.arange(n_pos, dtype=torch.float32)
+    # inv_freq on the host (the reference's module computes it at construction, device=None), the angle table on the target device:
+    # `_build_cache` runs cos/sin on x.device (rope_utils.py:191-205), and CUDA's cosf differs from glibc's by an ulp on some entries.
+    inv = _rope_inv_freq(d).to(device)
+    t = torch.arange(n_pos, device=device, dtype=torch.float32)
     freqs = torch.outer(t, inv)
     emb = torch.cat((freqs, freqs), dim=-1)
-    return emb.cos().to(torch.bfloat16).to(device), emb.sin().to(torch.bfloat16).to(device)
+    return emb.cos().to(torch.bfloat16), emb.sin().to(torch.bfloat16)
 
 
 def cu_seqlens_from_position_ids(position_ids: np.ndarray):

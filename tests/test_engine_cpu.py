@@ -174,6 +174,30 @@ def test_rope_config_resolution_follows_the_reference():
     assert torch.equal(a, b) and not torch.equal(a, _rope_inv_freq(legacy))
 
 
+def test_rope_tables_equal_the_reference_golden():
+    """engine._rope_inv_freq / rope_tables vs the reference's own `_compute_default_inv_freq` / `_compute_llama3_inv_freq` and
+    `LlamaRotaryEmbedding._build_cache` (components/models/llama/rope_utils.py:112-150, 191-205): golden vectors written by
+    tests/golden/gen_rope_golden.py from the unmodified reference, bit-exact (fp32 inv_freq, bf16 cos/sin).  The llama3_8b case is the
+    benchmark config's RoPE."""
+    import numpy as np
+    from automodel_b200.engine import _rope_inv_freq, rope_tables
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rope_golden.npz"))
+    l3 = {"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0}
+    cases = {
+        "llama3_8b": dict(hidden_size=4096, num_attention_heads=32, max_position_embeddings=8192, rope_theta=500000.0,
+                          rope_scaling=dict(l3, original_max_position_embeddings=8192)),
+        "default_hd64": dict(hidden_size=256, num_attention_heads=4, max_position_embeddings=512, rope_theta=10000.0),
+        "llama3_small_ctx": dict(hidden_size=256, num_attention_heads=2, max_position_embeddings=256, rope_theta=500000.0,
+                                 rope_scaling=dict(l3, original_max_position_embeddings=64)),
+    }
+    for name, kw in cases.items():
+        d = LlamaDims.from_hf(dict(vocab_size=512, intermediate_size=512, num_hidden_layers=1, num_key_value_heads=kw["num_attention_heads"], **kw))
+        assert np.array_equal(_rope_inv_freq(d).numpy(), z[name + "/inv_freq"]), name
+        cos, sin = rope_tables(d, 512, torch.device("cpu"))
+        assert cos.dtype == torch.bfloat16
+        assert np.array_equal(cos.float().numpy(), z[name + "/cos"]) and np.array_equal(sin.float().numpy(), z[name + "/sin"]), name
+
+
 def _hsdp_worker(rank, port, out_q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
