@@ -33,14 +33,15 @@ SIGNATURES = {
     "b200_sumsq_bf16": (_i, [_vp, _i64, _vp, _vp, _i, _vp]),
     "b200_adamw_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _vp, _i, _vp]),
     "b200_add_inplace_bf16": (_i, [_vp, _vp, _i64, _vp]),
-    "b200_mem_alloc": (_i, [C.POINTER(_vp), _sz]),
-    "b200_mem_free": (_i, [_vp]),
-    "b200_ipc_export": (_i, [_vp, _vp]),
-    "b200_ipc_import": (_i, [_vp, C.POINTER(_vp)]),
-    "b200_ipc_close": (_i, [_vp]),
-    "b200_copy_async": (_i, [_vp, _vp, _sz, _vp]),
-    "b200_reduce_scatter_pull_workspace_floats": (_i, []),
-    "b200_reduce_scatter_pull_bf16": (_i, [_vp, C.POINTER(_vp), _i, _i64, _vp, _i, _vp, _i, _vp]),
+    "b200_ctx_create": (_i, [C.POINTER(_vp), _i, _i]),
+    "b200_ctx_destroy": (_i, [_vp]),
+    "b200_ctx_set_timeout_ms": (_i, [_vp, _i64]),
+    "b200_ctx_signal_pad_bytes": (_sz, []),
+    "b200_ctx_set_signal_pad": (_i, [_vp, C.POINTER(_vp), _sz]),
+    "b200_ctx_register_buffer": (_i, [_vp, _i, C.POINTER(_vp), _vp, _sz]),
+    "b200_ctx_has_multicast": (_i, [_vp, _i]),
+    "b200_reducescatter_layer": (_i, [_vp, _i, _sz, _i64, _i, _i, _vp]),
+    "b200_allgather_layer": (_i, [_vp, _i, _sz, _i64, _i, _i, _vp]),
 }
 
 

@@ -47,14 +47,15 @@ int attn_fwd_tc(const void*, const void*, const void*, void*, float*, const int*
 int attn_bwd_tc(const void*, const void*, const void*, const void*, const void*, const float*, void*, void*, void*, void*, const int*, int,
                 int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, int, int, float, cudaStream_t);
 
-int mem_alloc(void**, size_t);
-int mem_free(void*);
-int ipc_export(void*, void*);
-int ipc_import(const void*, void**);
-int ipc_close(void*);
-int copy_async(void*, const void*, size_t, cudaStream_t);
-int reduce_scatter_pull_workspace_floats();
-int reduce_scatter_pull_bf16(void*, const void* const*, int, int64_t, float*, int, float*, int, cudaStream_t);
+struct CommCtx;
+int ctx_create(CommCtx**, int, int);
+int ctx_destroy(CommCtx*);
+int ctx_set_timeout_ms(CommCtx*, int64_t);
+int ctx_set_signal_pad(CommCtx*, void* const*, size_t);
+int ctx_register_buffer(CommCtx*, int, void* const*, void*, size_t);
+int ctx_has_multicast(const CommCtx*, int);
+int reducescatter_layer(CommCtx*, int, size_t, int64_t, int, int, cudaStream_t);
+int allgather_layer(CommCtx*, int, size_t, int64_t, int, int, cudaStream_t);
 
 int attn_fwd_tc64(const void*, const void*, const void*, void*, float*, const int*, int, int, int64_t, int64_t, int64_t, int64_t, int, int,
                   int, int, float, cudaStream_t);
@@ -213,16 +214,22 @@ int b200_adamw_step(void* p, const void* g, void* m, void* v, float* master, int
 }
 int b200_add_inplace_bf16(void* dst, const void* src, int64_t n, b200_stream_t stream) { return add_inplace_bf16(dst, src, n, S(stream)); }
 
-int b200_mem_alloc(void** ptr, size_t bytes) { return mem_alloc(ptr, bytes); }
-int b200_mem_free(void* ptr) { return mem_free(ptr); }
-int b200_ipc_export(void* ptr, void* handle64) { return ipc_export(ptr, handle64); }
-int b200_ipc_import(const void* handle64, void** ptr) { return ipc_import(handle64, ptr); }
-int b200_ipc_close(void* ptr) { return ipc_close(ptr); }
-int b200_copy_async(void* dst, const void* src, size_t bytes, b200_stream_t stream) { return copy_async(dst, src, bytes, S(stream)); }
-int b200_reduce_scatter_pull_workspace_floats(void) { return reduce_scatter_pull_workspace_floats(); }
-int b200_reduce_scatter_pull_bf16(void* dst, const void* const* srcs, int nsrc, int64_t n, float* norm_sq, int accumulate_norm,
-                                  float* workspace, int ctas, b200_stream_t stream) {
-  return reduce_scatter_pull_bf16(dst, srcs, nsrc, n, norm_sq, accumulate_norm, workspace, ctas, S(stream));
+int b200_ctx_create(b200_ctx** ctx, int rank, int world) { return ctx_create(reinterpret_cast<CommCtx**>(ctx), rank, world); }
+int b200_ctx_destroy(b200_ctx* ctx) { return ctx_destroy(reinterpret_cast<CommCtx*>(ctx)); }
+int b200_ctx_set_timeout_ms(b200_ctx* ctx, int64_t ms) { return ctx_set_timeout_ms(reinterpret_cast<CommCtx*>(ctx), ms); }
+int b200_ctx_set_signal_pad(b200_ctx* ctx, void* const* pads, size_t bytes) {
+  return ctx_set_signal_pad(reinterpret_cast<CommCtx*>(ctx), pads, bytes);
+}
+int b200_ctx_register_buffer(b200_ctx* ctx, int slot, void* const* peer_ptrs, void* multicast_ptr, size_t bytes) {
+  return ctx_register_buffer(reinterpret_cast<CommCtx*>(ctx), slot, peer_ptrs, multicast_ptr, bytes);
+}
+int b200_ctx_has_multicast(const b200_ctx* ctx, int slot) { return ctx_has_multicast(reinterpret_cast<const CommCtx*>(ctx), slot); }
+size_t b200_ctx_signal_pad_bytes(void) { return 2 * 64 * 8 * sizeof(uint32_t); }
+int b200_reducescatter_layer(b200_ctx* ctx, int slot, size_t byte_offset, int64_t shard_elems, int mode, int ctas, b200_stream_t stream) {
+  return reducescatter_layer(reinterpret_cast<CommCtx*>(ctx), slot, byte_offset, shard_elems, mode, ctas, S(stream));
+}
+int b200_allgather_layer(b200_ctx* ctx, int slot, size_t byte_offset, int64_t shard_elems, int mode, int ctas, b200_stream_t stream) {
+  return allgather_layer(reinterpret_cast<CommCtx*>(ctx), slot, byte_offset, shard_elems, mode, ctas, S(stream));
 }
 
 }  // extern "C"

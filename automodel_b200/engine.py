@@ -81,7 +81,9 @@ class _Streams:
 
     def __init__(self, device):
         self.cuda = device.type == "cuda"
-        self.comm = torch.cuda.Stream(device) if self.cuda else None
+        # high priority: a pending communication CTA (small: 512 threads, <= 64 registers, no smem) is placed before the next compute kernel's
+        # CTAs, next to which it then co-resides
+        self.comm = torch.cuda.Stream(device, priority=-1) if self.cuda else None
         self.opt = torch.cuda.Stream(device) if self.cuda else None
         self.wg = torch.cuda.Stream(device) if self.cuda else None    # weight-gradient GEMMs (see backward_from_dlogits)
 
@@ -103,7 +105,7 @@ class ShardedLlamaEngine:
 
     def __init__(self, cfg, device, process_group=None, max_tokens=4096, lr=1e-5, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1,
                  adam_mode=0, master_weights=False, ops=None, max_positions=None, reference_rounding=True, activation_checkpointing=False,
-                 replica_group=None):
+                 replica_group=None, reduce_dtype=None, comm=None):
         if ops is None:
             from . import ops as _ops  # raises if libb200_train.so is missing: no fallback
             ops = _ops
@@ -136,6 +138,10 @@ class ShardedLlamaEngine:
         self.n_params = total_params(self.units)
         self.max_tokens = max_tokens
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        if master_weights and adam_mode == 1:
+            # mode 1 reproduces torch.optim.AdamW on bf16 parameters op by op (every intermediate rounded to bf16): an fp32 master copy would
+            # be overwritten with the rounded value each step - it only makes sense with the fp32-math update
+            raise ValueError("master_weights=True needs adam_mode=0 (fp32 update math); adam_mode=1 is the bf16 torch.optim.AdamW sequence")
         self.adam_mode = adam_mode
         self.round_before_add = bool(reference_rounding)
         self.step_count = 0
@@ -156,30 +162,47 @@ class ShardedLlamaEngine:
         bf, dev = torch.bfloat16, self.device
 
         # ---- persistent flat storage
-        self.peer = None
         self._rs_started = False
-        # B200_PEER_COMM: "0" NCCL collectives (default) | "1" NVLink peer path for both collectives | "ag" hybrid: NCCL reduce-scatter,
-        # copy-engine all-gather (zero SMs next to the forward GEMMs)
-        peer_mode = os.environ.get("B200_PEER_COMM", "0")
-        self._peer_rs = peer_mode == "1"
-        if self.world > 1 and dev.type == "cuda" and peer_mode in ("1", "ag"):
-            if self.replicas > 1:
-                raise NotImplementedError("the NVLink peer-memory path is single-box full sharding; use the NCCL path with replica groups")
-            # NVLink peer-memory data path (csrc/comm.cu): parameters and gradients of all units live in two IPC-exported slabs
-            from .peer import Slab, PeerTable
+        # Gradient reduction precision (reference: MixedPrecisionPolicy.reduce_dtype, default float32, components/distributed/config.py:121-132):
+        # "float32" = fp32 accumulation across ranks with ONE rounding to the bf16 gradient, "bfloat16" = NCCL's bf16 ring (rounds per hop).
+        self.reduce_dtype = reduce_dtype or os.environ.get("B200_REDUCE_DTYPE", "float32")
+        if self.reduce_dtype not in ("float32", "bfloat16"):
+            raise ValueError(f"reduce_dtype {self.reduce_dtype!r}: float32 or bfloat16")
+        # Per-unit collectives.  "nvls": this repository's kernels on symmetric memory (b200_reducescatter_layer / b200_allgather_layer:
+        # NVSwitch multimem.ld_reduce with fp32 accumulation / multimem.st, peer loads where the platform has no multicast), always fp32
+        # accumulation; "p2p": the same entries forced onto the peer-load variant; "nccl": torch.distributed in-place collectives
+        # (multi-node / replica groups; fp32 reduction goes through an fp32 staging buffer).
+        self.comm = comm or os.environ.get("B200_COMM", "nccl")
+        if self.comm not in ("nccl", "nvls", "p2p"):
+            raise ValueError(f"comm {self.comm!r}: nccl, nvls or p2p")
+        self.sym = None
+        self._comm_ctas = int(os.environ.get("B200_COMM_CTAS", "32"))
+        if self.world > 1 and dev.type == "cuda" and self.comm in ("nvls", "p2p"):
+            from .symm import SymmetricSlab, CommContext
+            if self.world > 8:
+                raise NotImplementedError("the symmetric-memory data path spans one NVSwitch box (<= 8 ranks per shard group); use comm='nccl'")
             offs, tot = [], 0
             for u in self.units:
                 offs.append(tot)
                 tot += u.padded
             self._unit_off = offs
-            self._p_slab, self._g_slab = Slab(tot, dev), Slab(tot, dev)
+            self._p_slab, self._g_slab = SymmetricSlab(tot, bf, dev, process_group), SymmetricSlab(tot, bf, dev, process_group)
             self.p_full = [self._p_slab.tensor[o:o + u.padded] for o, u in zip(offs, self.units)]
             self.g_full = [self._g_slab.tensor[o:o + u.padded] for o, u in zip(offs, self.units)]
-            self.peer = (PeerTable(self._p_slab, process_group), PeerTable(self._g_slab, process_group))
-            self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+            self.sym = CommContext(process_group, dev)
+            self.sym.register(CommContext.PARAMS, self._p_slab)
+            self.sym.register(CommContext.GRADS, self._g_slab)
+            self._sym_mode = 1 if self.comm == "p2p" else 0
+            self.comm_kind = "nvls" if (self._sym_mode == 0 and self.sym.has_multicast(CommContext.GRADS)) else "p2p"
         else:
+            self.comm_kind = "nccl" if self.world > 1 else "none"
             self.p_full = [torch.zeros(u.padded, dtype=bf, device=dev) for u in self.units]   # unsharded params (shard lives inside)
             self.g_full = [torch.zeros(u.padded, dtype=bf, device=dev) for u in self.units]   # unsharded grads (RS in place)
+        self._rs32 = self._rs32_out = None
+        if self.world > 1 and self.sym is None and self.reduce_dtype == "float32":
+            big = max(u.padded for u in self.units)
+            self._rs32 = torch.empty(big, dtype=torch.float32, device=dev)
+            self._rs32_out = torch.empty(big // self.world, dtype=torch.float32, device=dev)
         self.m = [torch.zeros(u.padded // self.world, dtype=bf, device=dev) for u in self.units]
         self.v = [torch.zeros(u.padded // self.world, dtype=bf, device=dev) for u in self.units]
         self.master = [torch.zeros(u.padded // self.world, dtype=torch.float32, device=dev) for u in self.units] if master_weights else None
@@ -277,6 +300,9 @@ class ShardedLlamaEngine:
     def load_state_dict(self, sd):
         """sd: HF-named full tensors (torch or numpy, any float dtype).  Every rank loads the full model (the metric's
         random-init / a from_pretrained snapshot); optimizer shards start at zero."""
+        self.sync_params()      # a pending side-stream optimizer sweep / all-gather must not overwrite the freshly loaded weights
+        if self.streams.cuda:
+            torch.cuda.synchronize(self.device)
         with torch.no_grad():
             for name, dst in self.P.items():
                 src = sd[name]
@@ -310,6 +336,9 @@ class ShardedLlamaEngine:
 
     def load_optimizer_state(self, named, step_count):
         """Inverse of gather_optimizer_state: copy this rank's slice of every full (exp_avg, exp_avg_sq) into the flat shards."""
+        self.sync_params()
+        if self.streams.cuda:
+            torch.cuda.synchronize(self.device)
         with torch.no_grad():
             for ui, u in enumerate(self.units):
                 a, b = u.shard_range(self.rank, self.world)
@@ -360,21 +389,13 @@ class ShardedLlamaEngine:
         st = self.streams
         ev = st.event()
         st.record(ev)                       # shard update (AdamW) issued on the compute stream
-        if st.cuda and self.peer is not None:
-            # copy-engine push of the updated shard into every peer's parameter buffer (zero SMs), then a 4-byte all-reduce as the
-            # "everybody's pushes have landed" flag (stream-ordered behind the copies on every rank)
-            a, b = self.units[ui].shard_range(self.rank, self.world)
-            off = (self._unit_off[ui] + a) * 2
-            tab = self.peer[0]
-            # NOTE: issuing the N-1 pushes on separate streams (to spread them over the copy engines) was measured faster at N=2 but hung
-            # at N=8 (profiles/r1_n8_comm_paths.md); until that is understood the pushes stay on the single communication stream.
+        if st.cuda and self.sym is not None:
+            # our kernel on the symmetric parameter slab: NVLS multimem.st of the updated slice (or peer pulls); the cross-rank
+            # "everybody's slice has landed" barrier is inside the kernel
+            n_shard = self.units[ui].padded // self.world
             with torch.cuda.stream(st.comm):
                 st.wait(ev, st.comm)
-                cs = st.comm.cuda_stream
-                for k in range(1, self.world):
-                    j = (self.rank + k) % self.world
-                    self.ops.copy_async(tab.base[j] + off, tab.base[self.rank] + off, (b - a) * 2, cs)
-                dist.all_reduce(self._flag, group=self.pg)
+                self.ops.allgather_layer(self.sym.ptr, 0, self._unit_off[ui] * 2, n_shard, self._sym_mode, self._comm_ctas, st.comm.cuda_stream)
                 done = st.event()
                 st.record(done, st.comm)
                 self.ev_ag[ui] = done
@@ -426,18 +447,18 @@ class ShardedLlamaEngine:
         st = self.streams
         ev = st.event()
         st.record(ev)                       # this unit's gradients are complete on the compute stream
-        if st.cuda and self.peer is not None and self._peer_rs:
-            # 4-byte all-reduce = "unit ui's gradients are complete on every rank"; then ONE kernel pulls this rank's slice from all
-            # peers over NVLink, reduces in fp32, writes the bf16 shard in place and accumulates the shard's sum of squares.
-            a, b = self.units[ui].shard_range(self.rank, self.world)
-            off = (self._unit_off[ui] + a) * 2
-            tab = self.peer[1]
+        if st.cuda and self.sym is not None:
+            # ONE kernel: meets the peers (in-kernel barrier = "unit ui's gradients are complete on every rank"), reduces this rank's
+            # slice across all ranks with fp32 accumulation (NVSwitch multimem.ld_reduce, or peer loads in rank order) and writes the
+            # bf16 shard in place
+            n_shard = self.units[ui].padded // self.world
             with torch.cuda.stream(st.comm):
                 st.wait(ev, st.comm)
                 st.wait(wg, st.comm)
-                dist.all_reduce(self._flag, group=self.pg)
-                srcs = [tab.base[self.rank] + off] + [tab.base[(self.rank + k) % self.world] + off for k in range(1, self.world)]
-                self.ops.reduce_scatter_pull_(srcs[0], srcs, b - a, self.norm_sq, self._rs_started, self.device, ctas=64, stream=st.comm.cuda_stream)
+                self.ops.reducescatter_layer(self.sym.ptr, 1, self._unit_off[ui] * 2, n_shard, self._sym_mode, self._comm_ctas, st.comm.cuda_stream)
+                if self.replicas > 1:
+                    dist.all_reduce(self.shard(self.g_full, ui), op=dist.ReduceOp.SUM, group=self.rpg)
+                self.ops.sumsq_(self.shard(self.g_full, ui), self.norm_sq, accumulate=self._rs_started)
                 self._rs_started = True
                 done = st.event()
                 st.record(done, st.comm)
@@ -446,17 +467,29 @@ class ShardedLlamaEngine:
             with torch.cuda.stream(st.comm):
                 st.wait(ev, st.comm)
                 st.wait(wg, st.comm)
-                dist.reduce_scatter_tensor(self.shard(self.g_full, ui), self.g_full[ui], op=dist.ReduceOp.SUM, group=self.pg)
-                if self.replicas > 1:
-                    dist.all_reduce(self.shard(self.g_full, ui), op=dist.ReduceOp.SUM, group=self.rpg)
+                if self._rs32 is not None:
+                    # fp32 reduction as the reference's MixedPrecisionPolicy(reduce_dtype=float32): widen, reduce-scatter, ONE rounding
+                    n = self.units[ui].padded
+                    g32, o32 = self._rs32[:n], self._rs32_out[:n // self.world]
+                    g32.copy_(self.g_full[ui])
+                    dist.reduce_scatter_tensor(o32, g32, op=dist.ReduceOp.SUM, group=self.pg)
+                    if self.replicas > 1:
+                        dist.all_reduce(o32, op=dist.ReduceOp.SUM, group=self.rpg)
+                    self.shard(self.g_full, ui).copy_(o32)
+                else:
+                    dist.reduce_scatter_tensor(self.shard(self.g_full, ui), self.g_full[ui], op=dist.ReduceOp.SUM, group=self.pg)
+                    if self.replicas > 1:
+                        dist.all_reduce(self.shard(self.g_full, ui), op=dist.ReduceOp.SUM, group=self.rpg)
                 self.ops.sumsq_(self.shard(self.g_full, ui), self.norm_sq, accumulate=self._rs_started)  # grad-norm partial, off the critical path
                 self._rs_started = True
                 done = st.event()
                 st.record(done, st.comm)
                 self.ev_rs[ui] = done
         else:
-            out = torch.empty_like(self.shard(self.g_full, ui))
-            dist.reduce_scatter_tensor(out, self.g_full[ui].clone(), op=dist.ReduceOp.SUM, group=self.pg)
+            wide = self.reduce_dtype == "float32"
+            src = self.g_full[ui].float() if wide else self.g_full[ui].clone()
+            out = torch.empty(src.numel() // self.world, dtype=src.dtype, device=src.device)
+            dist.reduce_scatter_tensor(out, src, op=dist.ReduceOp.SUM, group=self.pg)
             if self.replicas > 1:
                 dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.rpg)
             self.shard(self.g_full, ui).copy_(out)
@@ -480,8 +513,9 @@ class ShardedLlamaEngine:
     def __del__(self):
         try:
             self.close()
-        except Exception:
-            pass
+        except Exception as e:  # noqa: BLE001 - a destructor must not raise, but a failed drain (sticky CUDA error) must not vanish either
+            import sys
+            sys.stderr.write(f"ShardedLlamaEngine.close() failed during destruction: {type(e).__name__}: {e}\n")
 
     def set_stream_overlap(self, on: bool):
         """Measurement aid: with overlap off every kernel of the step runs back to back on the compute stream (weight-gradient GEMMs and
@@ -507,6 +541,10 @@ class ShardedLlamaEngine:
         T = b * S
         if T > self.max_tokens:
             raise ValueError(f"micro-batch of {T} tokens exceeds max_tokens={self.max_tokens}")
+        if S > self.cos.shape[0]:
+            # the RoPE kernel indexes the cos/sin tables by the position inside the row; the reference regrows its cache instead
+            # (rope_utils.py:224-226) - here the tables are sized once, from max_positions / max_position_embeddings
+            raise ValueError(f"rows of {S} tokens exceed the RoPE tables ({self.cos.shape[0]} positions): raise max_positions")
         if self.streams.cuda and input_ids.device == self.device:
             k = self._in_idx
             self._in_idx ^= 1
@@ -779,7 +817,7 @@ class ShardedLlamaEngine:
             if self.ev_rs[ui] is not None:
                 self.streams.wait(self.ev_rs[ui])
                 self.ev_rs[ui] = None
-            if not fused_norm:  # the pull kernel of the peer path already accumulated the shard's sum of squares
+            if not fused_norm:
                 ops.sumsq_(self.shard(self.g_full, ui), self.norm_sq, accumulate=ui > 0)
         if fused_norm:
             self._rs_started = False

@@ -274,21 +274,15 @@ def add_(dst, src):
     return dst
 
 
-def copy_async(dst_ptr, src_ptr, nbytes, stream=None):
-    """Copy-engine copy between raw device pointers (peer-to-peer over NVLink when they live on different GPUs)."""
-    check(lib().b200_copy_async(dst_ptr, src_ptr, nbytes, stream if stream is not None else _st()), "b200_copy_async")
+def reducescatter_layer(ctx, slot, byte_offset, shard_elems, mode=0, ctas=32, stream=None):
+    """In-place reduce-scatter of one unit of a registered symmetric buffer (fp32 accumulation, one rounding); see include/b200_train.h."""
+    check(lib().b200_reducescatter_layer(ctx, int(slot), int(byte_offset), int(shard_elems), int(mode), int(ctas),
+                                         stream if stream is not None else _st()), "b200_reducescatter_layer")
+    _count(1)
 
 
-_rs_ws = {}
-
-
-def reduce_scatter_pull_(dst_ptr, src_ptrs, n, norm_sq, accumulate_norm, device, ctas=32, stream=None):
-    """dst[i] = bf16(sum_j src_j[i]) (fp32 accumulate, source order), norm_sq (=|+=) sum of squares of the result."""
-    import ctypes as C
-    ws = _rs_ws.get(device)
-    if ws is None:
-        ws = _rs_ws[device] = torch.empty(lib().b200_reduce_scatter_pull_workspace_floats(), dtype=torch.float32, device=device)
-    arr = (C.c_void_p * len(src_ptrs))(*src_ptrs)
-    check(lib().b200_reduce_scatter_pull_bf16(dst_ptr, arr, len(src_ptrs), int(n), _p(norm_sq), int(accumulate_norm), ws.data_ptr(), int(ctas),
-                                              stream if stream is not None else _st()), "b200_reduce_scatter_pull_bf16")
-    _count(2 if norm_sq is not None else 1)
+def allgather_layer(ctx, slot, byte_offset, shard_elems, mode=0, ctas=32, stream=None):
+    """In-place all-gather of one unit of a registered symmetric buffer."""
+    check(lib().b200_allgather_layer(ctx, int(slot), int(byte_offset), int(shard_elems), int(mode), int(ctas),
+                                     stream if stream is not None else _st()), "b200_allgather_layer")
+    _count(1)

@@ -50,7 +50,9 @@ class B200ShardedConfig:
     fsdp2_forward_prefetch_depth: int = 1
     enable_compile: bool = False
     patch_is_packed_sequence: bool = False
-    mp_policy: Optional[object] = None       # only bf16 parameters / compute (the reduce-scatter runs in bf16 with fp32 accumulation per pair)
+    mp_policy: Optional[object] = None       # MixedPrecisionPolicy: param_dtype must be bf16; reduce_dtype (float32 | bfloat16) is honoured
+    reduce_dtype: Optional[str] = None       # gradient reduction precision; None = mp_policy.reduce_dtype, else float32 (FSDP2Config's default policy)
+    comm: Optional[str] = None               # per-unit collectives: nvls (own kernels on symmetric memory) | p2p | nccl; None = B200_COMM / default
     sequence_parallel: bool = False
     tp_plan: Optional[dict] = None
     offload_policy: Optional[object] = None
@@ -65,6 +67,17 @@ class B200ShardedConfig:
         pd = getattr(self.mp_policy, "param_dtype", None)
         if pd is not None and pd != torch.bfloat16:
             raise ValueError(f"strategy b200_sharded computes in bf16; mp_policy.param_dtype={pd} is not supported")
+        # components/distributed/config.py:121-132: the default policy reduces gradients in fp32
+        names = {torch.float32: "float32", torch.bfloat16: "bfloat16", "float32": "float32", "bfloat16": "bfloat16", "fp32": "float32", "bf16": "bfloat16"}
+        rd = self.reduce_dtype if self.reduce_dtype is not None else getattr(self.mp_policy, "reduce_dtype", None)
+        if rd is None:
+            rd = "float32"
+        if rd not in names:
+            raise ValueError(f"strategy b200_sharded reduces gradients in float32 or bfloat16; reduce_dtype={rd} is not supported")
+        self.reduce_dtype = names[rd]
+        od = getattr(self.mp_policy, "output_dtype", None)
+        if od is not None and od != torch.bfloat16:
+            raise ValueError(f"strategy b200_sharded produces bf16 activations; mp_policy.output_dtype={od} is not supported")
 
 
 class _Fwd(torch.autograd.Function):
@@ -326,22 +339,33 @@ class B200FusedAdamW(torch.optim.Optimizer):
     # ---- optimizer state in torch.optim form (what torch.distributed.checkpoint's get/set_optimizer_state_dict and therefore the
     # reference's Checkpointer read and write, components/checkpoint/stateful_wrappers.py): per-parameter "step" / "exp_avg" /
     # "exp_avg_sq".  `self.state` must never be empty, or DCP "initialises" it by running a throw-away optimizer.step().
-    def _refresh_state(self):
-        named = self.engine.gather_optimizer_state()
+    def _refresh_state(self, full=False):
+        """World 1: live views of the flat moment shards (zero copy).  World N: `self.state` holds only per-parameter placeholders (the
+        shared step counter + zero-size moments) so that nothing replicated stays resident - the full moments (2 x model bytes) are
+        all-gathered only for the duration of a `state_dict()` call (checkpoint time) and live exactly as long as the caller keeps the
+        returned dict."""
         self._step_t = torch.tensor(float(self.engine.step_count))   # ONE tensor shared by every parameter's state entry
         owner = self._owner()
         by_param = {id(p): n for n, p in owner._hf.items()} if owner is not None else {}
+        sharded = self.engine.world > 1
+        named = self.engine.gather_optimizer_state() if (full or not sharded) else None
         for group in self.param_groups:
             for p in group["params"]:
                 name = by_param.get(id(p))
                 if name is None:
                     continue
-                m, v = named[name]
+                if named is not None:
+                    m, v = named[name]
+                else:
+                    m = v = p.new_empty(0)
                 self.state[p] = {"step": self._step_t, "exp_avg": m, "exp_avg_sq": v}
 
     def state_dict(self):
-        self._refresh_state()
-        return super().state_dict()
+        self._refresh_state(full=True)
+        sd = super().state_dict()
+        if self.engine.world > 1:
+            self._refresh_state(full=False)      # drop this object's references to the gathered copies
+        return sd
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
@@ -349,11 +373,11 @@ class B200FusedAdamW(torch.optim.Optimizer):
         named, step = {}, self.engine.step_count
         for n, p in (owner._hf.items() if owner is not None else []):
             st = self.state.get(p)
-            if st and "exp_avg" in st:
+            if st and "exp_avg" in st and st["exp_avg"].numel() == p.numel():
                 named[n] = (st["exp_avg"], st["exp_avg_sq"])
                 step = int(float(st["step"]))
         self.engine.load_optimizer_state(named, step)
-        self._refresh_state()     # world 1: back to live views of the flat shards
+        self._refresh_state()     # world 1: back to live views of the flat shards; world N: placeholders
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -398,7 +422,8 @@ class B200ShardedManager:
         eng = ShardedLlamaEngine(cfg_d, dev, process_group=self.pg, max_tokens=self.config.max_tokens,
                                  adam_mode=self.config.adam_mode, master_weights=self.config.master_weights,
                                  reference_rounding=self.config.reference_rounding, max_positions=self.config.max_positions,
-                                 activation_checkpointing=self.config.activation_checkpointing, replica_group=self.rpg, ops=self.ops, **od)
+                                 activation_checkpointing=self.config.activation_checkpointing, replica_group=self.rpg, ops=self.ops,
+                                 reduce_dtype=self.config.reduce_dtype, comm=self.config.comm, **od)
         if hasattr(model, "named_parameters"):
             sd = model.state_dict()
             if sd and all(getattr(v, "device", torch.device("cpu")).type != "meta" for v in sd.values()):

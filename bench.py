@@ -2,8 +2,9 @@
 """Headline benchmark: tokens/sec of the sharded-DP training step, Llama-3-8B config, bf16, seq 4096, synthetic tokens.
 
   python bench.py --gpus N --steps K --warmup W            our sm_100a path (torchrun launches N ranks for N>1)
-  python bench.py --impl reference --gpus N ...            reference arm: the CPU restatement of the reference's step
-                                                           (oracle/, numpy on the host cores), bounded sample
+  python bench.py --impl reference --gpus N ...            reference arm: the UNMODIFIED reference recipe (baseline/_ref install) on
+                                                           the host cores, CPU/gloo, bounded sample (falls back to the numpy
+                                                           restatement in oracle/ when the install is absent)
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what each field means.
 """
@@ -83,12 +84,39 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
-def run_cpu_reference(steps, warmup, budget_s=150.0, quiet=False):
-    """Times the CPU restatement of the reference's training step (oracle/llama_step.py: numpy, all host threads BLAS can use)
-    on a bounded sample of the workload: Llama-3-8B layer dimensions (hidden 4096, ffn 14336, 32/8 heads of 128), ONE decoder layer,
-    vocab 2048, seq 512, b=1, fp32 (the reference's CPU/gloo recipe computes in fp32 on CPU), full step = fwd + bwd + clip + AdamW.
-    Reported tokens/s is converted to the full workload by the reference's FLOPs formula:
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count()
+
+
+def run_cpu_reference(steps, warmup, budget_s=150.0):
+    """The reference's own CPU implementation of the path, timed on the host cores on a bounded sample of the workload.
+
+    kind "reference" (baseline/_ref present): the UNMODIFIED `TrainFinetuneRecipeForNextTokenPrediction` over CPU/gloo, world size 1, in a
+    subprocess (baseline/run_ref_cpu.py): Llama-3-8B layer dimensions, ONE decoder layer, vocab 2048, seq 512, b=1, fp32, full optimizer
+    steps, every host thread torch uses.  kind "port" (no install): the numpy restatement oracle/llama_step.py on the same sample.
+    Either way tokens/s is converted to the full workload by the reference's FLOPs formula (components/utils/flops_utils.py:51-78):
         tokens/s(8B, S=4096) = achieved CPU FLOP/s / 4.825e10."""
+    f_full = flops_per_token(LLAMA3_8B, SEQ)
+    runner = os.path.join(ROOT, "baseline", "run_ref_cpu.py")
+    if os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "nemo_automodel")):
+        try:
+            r = subprocess.run([sys.executable, runner, str(steps), str(warmup), str(budget_s)], capture_output=True, text=True,
+                               timeout=budget_s + 300, cwd=ROOT)
+            lines = [l for l in r.stdout.splitlines() if l.startswith("REF_CPU_RESULT ")]
+            if r.returncode == 0 and lines:
+                d = json.loads(lines[-1][len("REF_CPU_RESULT "):])
+                cpu_flops = d["flops_per_step"] / d["mean_step_s"]
+                return {"value": cpu_flops / f_full, "unit": "tokens/s", "cores": d["cores"], "threads": d["threads"], "kind": "reference",
+                        "sample": f"unmodified reference recipe ({d['model_class']} + torch.optim.{d['optimizer_class']} + MaskedCrossEntropy, CPU/gloo, fp32) on 1 decoder "
+                                  f"layer of Llama-3-8B dims, vocab {d['vocab']}, seq {d['seq']}, b=1: {d['mean_step_s'] * 1e3:.0f} ms/step over {d['steps_timed']} steps "
+                                  f"= {cpu_flops / 1e9:.1f} GFLOP/s; scaled to 8B/seq4096 by the reference FLOPs formula",
+                        "ms_per_sample_step": d["mean_step_s"] * 1e3, "steps_timed": d["steps_timed"], "cpu_gflops": cpu_flops / 1e9}
+            sys.stderr.write("reference CPU run failed, falling back to the numpy port:\n" + r.stderr[-2000:] + "\n")
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"reference CPU run failed ({e}); falling back to the numpy port\n")
     import numpy as np
     from oracle import llama_step as O
     from oracle.portable_init import llama_param_shapes
@@ -103,23 +131,16 @@ def run_cpu_reference(steps, warmup, budget_s=150.0, quiet=False):
     f_tok = flops_per_token(cfg, S)
     times = []
     t_start = time.perf_counter()
-    done = 0
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         O.train_step(params, opt, cfg, mb, prec="fp32", max_grad_norm=1.0, timing=True)
-        dt = time.perf_counter() - t0
         if i >= warmup:
-            times.append(dt); done += 1
-        if time.perf_counter() - t_start > budget_s and done >= 1:
+            times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s and times:
             break
     mean = sum(times) / len(times)
     cpu_flops = f_tok * S / mean
-    tok_s_full = cpu_flops / flops_per_token(LLAMA3_8B, SEQ)
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        cores = os.cpu_count()
-    return {"value": tok_s_full, "unit": "tokens/s", "cores": cores, "kind": "port",
+    return {"value": cpu_flops / f_full, "unit": "tokens/s", "cores": _host_cores(), "kind": "port",
             "sample": f"oracle (numpy fp32) full train step on 1 decoder layer of Llama-3-8B dims, vocab 2048, seq {S}, b=1: "
                       f"{mean * 1e3:.0f} ms/step over {len(times)} steps = {cpu_flops / 1e9:.1f} GFLOP/s; scaled to 8B/seq4096 by the reference FLOPs formula",
             "ms_per_sample_step": mean * 1e3, "steps_timed": len(times), "cpu_gflops": cpu_flops / 1e9}
@@ -140,10 +161,13 @@ def _emit(saved_fd, line):
 
 
 def main():
-    # watchdog: a wedged collective must not hold a multi-GPU box until the driver's own limit (SIGALRM's default action terminates
-    # the process even while it is blocked inside a CUDA / NCCL call)
-    import signal
-    signal.alarm(int(os.environ.get("B200_BENCH_WATCHDOG_S", "900")))
+    # watchdog: a wedged collective must not hold a multi-GPU box until the driver's own limit.  faulthandler's timer thread works even
+    # while the main thread is blocked inside a CUDA / NCCL call: it writes every thread's Python stack to stderr (which rank, which
+    # call) and then terminates the process, so the peers' NCCL / in-kernel barriers time out instead of spinning silently.
+    import faulthandler
+    wd = int(os.environ.get("B200_BENCH_WATCHDOG_S", "900"))
+    sys.stderr.write(f"[bench rank {os.environ.get('RANK', '0')}] watchdog armed: {wd} s\n")
+    faulthandler.dump_traceback_later(wd, exit=True)
     saved_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -152,9 +176,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--layers", type=int, default=None, help="debug only: fewer layers (result is then NOT the headline metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-api", default="engine", choices=["engine", "facade"],
-                    help="public call timed by the e2e leg: ShardedLlamaEngine.train_step (default) or the reference-facing facade "
-                         "(B200CausalLM -> B200MaskedCrossEntropy -> backward -> clip -> B200FusedAdamW.step, what the reference recipe drives)")
+    ap.add_argument("--e2e-api", default="facade", choices=["engine", "facade"],
+                    help="public call timed by the e2e leg: the reference-facing facade (default: B200CausalLM -> B200MaskedCrossEntropy -> backward "
+                         "-> clip -> B200FusedAdamW.step, the call sequence of the reference recipe) or ShardedLlamaEngine.train_step")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1 only: skip the correctness block that precedes the timed region")
     ap.add_argument("--profile", action="store_true", help="for ncu runs only: 1 warm-up step, no e2e leg, no CPU baseline (numbers printed are NOT bench values)")
     ap.add_argument("--adam-mode", type=int, default=1, help="1 = torch.optim.AdamW bf16 op sequence (reference default optimizer), 0 = fp32 math")
     args = ap.parse_args()
@@ -193,6 +218,23 @@ def main():
         cfg["num_hidden_layers"] = args.layers
     eng = ShardedLlamaEngine(cfg, dev, process_group=pg, max_tokens=SEQ, lr=1e-5, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1,
                              adam_mode=args.adam_mode, max_positions=SEQ)
+    # ---- N > 1: correctness of the multi-GPU path, in the driver-visible record (the GPU test box has one GPU).  (1) the production
+    # collectives on one full-size decoder-layer unit of THIS engine vs fp32 NCCL references; (2) 10 optimizer steps of a small Llama
+    # sharded over the N ranks vs one rank accumulating the same sequences.  Out of tolerance = the run fails (rc 3), no number printed.
+    parity = None
+    if world > 1 and not args.no_parity and not args.profile:
+        from automodel_b200 import diagnostics
+        col = diagnostics.check_collectives(eng, unit_index=1)
+        par = diagnostics.check_sharded_step_parity(pg, dev, steps=10)
+        ok = (col["ag_bit_exact"] and col["rs_norm_sq_rel_err"] < 1e-5 and par["ranks_agree"] and par["max_abs_dloss"] <= 1e-3
+              and par["max_rel_dgnorm"] <= 2e-2 and (col["reduce_dtype"] != "float32" or col["rs_max_bf16_ulp_vs_fp32_allreduce"] <= 1))
+        parity = dict(par, collectives=col, ok=bool(ok), tolerance={"max_abs_dloss": 1e-3, "max_rel_dgnorm": 2e-2, "rs_bf16_ulp": 1})
+        if not ok:
+            sys.stderr.write(f"[bench rank {rank}] N={world} parity block FAILED: {json.dumps(parity)}\n")
+            if rank == 0:
+                _emit(saved_stdout, {"metric": METRIC, "n_gpus": world, "parity": parity, "error": "multi-GPU parity block out of tolerance; no throughput reported"})
+            dist.destroy_process_group()
+            return 3
     eng.init_random_(seed=1234)
 
     # synthetic tokens, MockIterableDataset semantics (components/datasets/llm/mock_iterable_dataset.py:41-59); every rank draws its own
@@ -360,11 +402,14 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "llama3_8b_sft_seq4096_b1_per_gpu", "layers": cfg["num_hidden_layers"], "global_batch": world, "seq_len": SEQ,
-                       "parallelism": f"sharded-dp{world}", "grad_accum": 1, "optimizer": "AdamW(bf16 states)" if args.adam_mode == 1 else "AdamW(fp32 math)",
+                       "parallelism": f"sharded-dp{world}", "collectives": eng.comm_kind,
+                       "grad_reduce": ("fp32 accumulate" if (eng.sym is not None or eng.reduce_dtype == "float32") else "bf16") if world > 1 else "none", "grad_accum": 1, "optimizer": "AdamW(bf16 states)" if args.adam_mode == 1 else "AdamW(fp32 math)",
                        "clip_grad_norm": 1.0, "l2": "working set (16 GB params + 16 GB grads + activations) >> 126 MB L2; no flush needed",
                        "tokens_per_step": tokens_per_step},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "final_loss": final_loss, "final_grad_norm": final_gnorm,
             "flops_per_token": f_tok, "host_issue_ms_per_step": host_issue_ms, "host_enqueue_ms_idle_gpu": host_only_ms}
+    if parity is not None:
+        line["parity"] = parity
     if args.profile:
         line["profile_mode"] = True
     if not args.no_cpu_baseline and not args.profile and world == 1:

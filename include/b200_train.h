@@ -109,21 +109,32 @@ int b200_adamw_step(void* p, const void* g, void* m, void* v, float* master, int
 /* dst += src (bf16), gradient accumulation helper */
 int b200_add_inplace_bf16(void* dst, const void* src, int64_t n, b200_stream_t stream);
 
-/* ---- NVLink peer-memory data path (replaces FSDP2's NCCL reduce_scatter / all_gather,
- * torch/distributed/fsdp/_fully_shard/_fsdp_collectives.py:237-291,448-664 as set up by components/distributed/parallelizer.py:858-872).
- * Buffers peers touch are allocated here (cudaMalloc) and exported/imported with CUDA IPC (64-byte handles). */
-int b200_mem_alloc(void** ptr, size_t bytes);
-int b200_mem_free(void* ptr);
-int b200_ipc_export(void* ptr, void* handle64);
-int b200_ipc_import(const void* handle64, void** ptr);
-int b200_ipc_close(void* ptr);
-/* copy-engine copy (peer-to-peer over NVLink when dst/src live on different GPUs): the all-gather push, zero SMs */
-int b200_copy_async(void* dst, const void* src, size_t bytes, b200_stream_t stream);
-/* reduce-scatter pull: dst[i] = bf16(sum_j srcs[j][i]) with fp32 accumulation in source order (srcs[0] = own slice, may alias dst;
- * srcs[1..] = peer-mapped views of the same slice); norm_sq[0] (=|+=) sum of squares of the result (grad-norm fused in). */
-int b200_reduce_scatter_pull_workspace_floats(void);
-int b200_reduce_scatter_pull_bf16(void* dst, const void* const* srcs, int nsrc, int64_t n, float* norm_sq, int accumulate_norm,
-                                  float* workspace, int ctas, b200_stream_t stream);
+/* ---- per-unit collectives of the sharded step on NVLink 5 / NVSwitch (replace FSDP2's NCCL all_gather_into_tensor / reduce_scatter_tensor,
+ * torch/distributed/fsdp/_fully_shard/_fsdp_collectives.py:237-291,448-664, as set up by components/distributed/parallelizer.py:858-872
+ * with MixedPrecisionPolicy(param bf16, reduce fp32), components/distributed/config.py:121-132).
+ * b200_ctx: one per rank; owns no memory.  The caller registers SYMMETRIC buffers (the same allocation on every rank of one NVSwitch
+ * box, e.g. from torch.distributed._symmetric_memory): peer_ptrs[j] = this rank's mapping of rank j's buffer (peer_ptrs[rank] = the
+ * local pointer), multicast_ptr = the NVLS multicast mapping of the buffer or NULL, plus one zero-initialised symmetric signal pad of
+ * b200_ctx_signal_pad_bytes() bytes.  A unit is world*shard_elems bf16 values at byte_offset of a registered buffer; rank r owns
+ * elements [r*shard_elems, (r+1)*shard_elems).
+ *   b200_reducescatter_layer: in place; the owner's slice := bf16(sum over ranks, fp32 accumulation, ONE rounding) - NVLS
+ *       multimem.ld_reduce(.acc::f32) when the buffer has a multicast mapping (mode 0), 16-byte peer loads summed in rank order otherwise
+ *       (or mode 1).  The other slices of the local buffer are left as they were.
+ *   b200_allgather_layer: in place; every rank's slice is replicated into every rank's buffer (NVLS multimem.st, or peer pulls).
+ * Cross-rank ordering is inside the kernels (CTA-to-CTA release/acquire flags on the signal pad): each rank launches the entry on its
+ * own stream behind the work that produces its contribution; all ranks must launch the same entries in the same order with the same
+ * `ctas` (1..64).  No host synchronisation, no NCCL.  A rank that never arrives makes the peers' kernels trap after the ctx timeout
+ * (default 60 s) instead of hanging. */
+typedef struct b200_ctx b200_ctx;
+int b200_ctx_create(b200_ctx** ctx, int rank, int world); /* world <= 8 */
+int b200_ctx_destroy(b200_ctx* ctx);
+int b200_ctx_set_timeout_ms(b200_ctx* ctx, int64_t ms);
+size_t b200_ctx_signal_pad_bytes(void);
+int b200_ctx_set_signal_pad(b200_ctx* ctx, void* const* pads, size_t bytes);
+int b200_ctx_register_buffer(b200_ctx* ctx, int slot, void* const* peer_ptrs, void* multicast_ptr, size_t bytes); /* slot 0..3 */
+int b200_ctx_has_multicast(const b200_ctx* ctx, int slot);
+int b200_reducescatter_layer(b200_ctx* ctx, int slot, size_t byte_offset, int64_t shard_elems, int mode, int ctas, b200_stream_t stream);
+int b200_allgather_layer(b200_ctx* ctx, int slot, size_t byte_offset, int64_t shard_elems, int mode, int ctas, b200_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,7 @@
-"""Multi-GPU parity of the sharded step (NCCL, world size 2): in-place reduce-scatter / all-gather on the flat buffers.
-Skipped on a single-GPU box; the same orchestration is covered on CPU over gloo in tests/test_engine_cpu.py."""
+"""Multi-GPU parity of the sharded step on real GPUs (world size 2, or every visible GPU with B200_TEST_WORLD): the per-unit collectives
+(own NVLS / peer-load kernels on symmetric memory, and the NCCL fallback with fp32 or bf16 reduction) and the sharded step built on them.
+Skipped on a single-GPU box - bench.py carries the same checks in its `parity` block for exactly that reason; the orchestration is also
+covered on CPU over gloo in tests/test_engine_cpu.py."""
 import os
 import pytest
 import torch
@@ -9,18 +11,25 @@ pytestmark = pytest.mark.gpu
 
 from tests.golden_utils import load, model_cfg, init_params, batches  # noqa: E402
 
+MODES = [("nvls", "float32"), ("p2p", "float32"), ("nccl", "float32"), ("nccl", "bfloat16")]
+IDS = [f"{c}-{r}" for c, r in MODES]
 
-def _worker(rank, world, port, out_q, peer_comm="1"):
-    os.environ["B200_PEER_COMM"] = peer_comm
+
+def _init(rank, world, port):
     import torch.distributed as dist
-    from automodel_b200.engine import ShardedLlamaEngine
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    return dist
+
+
+def _fixture_worker(rank, world, port, out_q, comm, reduce_dtype):
+    dist = _init(rank, world, port)
+    from automodel_b200.engine import ShardedLlamaEngine
     z, meta = load("tiny_bf16")
     cfg = model_cfg(meta); oc = meta["optimizer"]
     eng = ShardedLlamaEngine(cfg, f"cuda:{rank}", process_group=dist.group.WORLD, max_tokens=meta["config"]["seq"], lr=oc["lr"],
-                             betas=tuple(oc["betas"]), eps=oc["eps"], weight_decay=oc["weight_decay"], adam_mode=1)
+                             betas=tuple(oc["betas"]), eps=oc["eps"], weight_decay=oc["weight_decay"], adam_mode=1, comm=comm, reduce_dtype=reduce_dtype)
     eng.load_state_dict(init_params(meta))
     res = []
     for s in range(10):
@@ -33,31 +42,71 @@ def _worker(rank, world, port, out_q, peer_comm="1"):
     dist.all_gather(gathered, flat)
     same = all(torch.equal(gathered[0], t) for t in gathered)
     if rank == 0:
-        out_q.put((res, same))
+        out_q.put((res, same, eng.comm_kind))
     dist.barrier()
     dist.destroy_process_group()
 
 
-_MODES = [("1", "nvlink_peer_path"), ("0", "nccl_collectives")]
-if os.environ.get("B200_TEST_EXPERIMENTAL") == "1":     # written after the last multi-GPU run of round 1: opt-in until it has passed once
-    _MODES.append(("ag", "nccl_rs_copy_engine_ag"))
+def _selfcheck_worker(rank, world, port, out_q, comm, reduce_dtype):
+    dist = _init(rank, world, port)
+    from automodel_b200.engine import ShardedLlamaEngine
+    from automodel_b200 import diagnostics as D
+    # one 8B-sized decoder layer + a small vocabulary: the collectives see the benchmark's 218 M-element unit
+    cfg = {"vocab_size": 1024, "hidden_size": 4096, "intermediate_size": 14336, "num_hidden_layers": 1, "num_attention_heads": 32,
+           "num_key_value_heads": 8, "max_position_embeddings": 256, "rms_norm_eps": 1e-5, "rope_theta": 500000.0}
+    eng = ShardedLlamaEngine(cfg, f"cuda:{rank}", process_group=dist.group.WORLD, max_tokens=256, comm=comm, reduce_dtype=reduce_dtype)
+    col = D.check_collectives(eng, unit_index=1)
+    eng.close()
+    del eng
+    par = D.check_sharded_step_parity(dist.group.WORLD, f"cuda:{rank}", steps=10, comm=comm, reduce_dtype=reduce_dtype)
+    if rank == 0:
+        out_q.put((col, par))
+    dist.barrier()
+    dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("peer_comm", [m for m, _ in _MODES], ids=[i for _, i in _MODES])
-def test_world2_matches_reference_curve(peer_comm):
+def _spawn(target, world, *args):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 1000) + (7 if peer_comm == "0" else 0)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, peer_comm)) for r in range(2)]
+    port = 29700 + (os.getpid() * 7 + hash(args) % 97) % 2000
+    procs = [ctx.Process(target=target, args=(r, world, port, q) + args) for r in range(world)]
     for p in procs:
         p.start()
-    res, same = q.get(timeout=600)
+    out = q.get(timeout=600)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    return out
+
+
+def _world():
+    return int(os.environ.get("B200_TEST_WORLD", "2"))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("comm,reduce_dtype", MODES, ids=IDS)
+def test_world2_matches_reference_curve(comm, reduce_dtype):
+    """The reference's own 2-sequence steps (tiny_bf16 fixture, produced by the unmodified recipe) with one sequence per rank."""
+    res, same, kind = _spawn(_fixture_worker, 2, comm, reduce_dtype)
     assert same, "ranks disagree on the gathered parameters after the in-place all-gather"
     _, meta = load("tiny_bf16")
     for s, (l, g) in enumerate(res):
-        assert abs(l - meta["loss"][s]) < 1e-3, (s, l, meta["loss"][s])
-        assert abs(g - meta["grad_norm"][s]) < 2e-2 * meta["grad_norm"][s], (s, g, meta["grad_norm"][s])
+        assert abs(l - meta["loss"][s]) < 1e-3, (kind, s, l, meta["loss"][s])
+        assert abs(g - meta["grad_norm"][s]) < 2e-2 * meta["grad_norm"][s], (kind, s, g, meta["grad_norm"][s])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("comm,reduce_dtype", MODES, ids=IDS)
+def test_collectives_and_sharded_step_selfcheck(comm, reduce_dtype):
+    """Collectives on an 8B-sized unit vs fp32 NCCL references (fp32 reduction: within 1 bf16 ulp, bit-exact all-gather), and the sharded
+    step vs one rank accumulating the same sequences."""
+    world = min(_world(), torch.cuda.device_count())
+    col, par = _spawn(_selfcheck_worker, world, comm, reduce_dtype)
+    print(col, par)
+    assert col["ag_bit_exact"], col
+    assert col["rs_norm_sq_rel_err"] < 1e-5, col
+    if reduce_dtype == "float32":
+        assert col["rs_max_bf16_ulp_vs_fp32_allreduce"] <= 1, col
+        assert col["rs_frac_not_bit_equal"] < 1e-3, col
+    assert par["ranks_agree"], par
+    assert par["max_abs_dloss"] < 1e-3 and par["max_rel_dgnorm"] < 2e-2, par

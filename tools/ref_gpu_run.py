@@ -44,7 +44,7 @@ model:
     rope_theta: {theta}
 {rope_scaling}    tie_word_embeddings: false
     architectures: [LlamaForCausalLM]
-  torch_dtype: bfloat16
+  torch_dtype: {dtype}
   attn_implementation: {attn}
   use_liger_kernel: false
 checkpoint: {{enabled: false}}
@@ -101,8 +101,13 @@ def run(args):
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    if args.sdpa_backend:      # restrict torch SDPA to one backend (reference self-noise runs: same model, another attention kernel)
+        torch.backends.cuda.enable_flash_sdp(args.sdpa_backend == "flash")
+        torch.backends.cuda.enable_cudnn_sdp(args.sdpa_backend == "cudnn")
+        torch.backends.cuda.enable_mem_efficient_sdp(args.sdpa_backend == "efficient")
+        torch.backends.cuda.enable_math_sdp(args.sdpa_backend == "math")
     c = dict(CONFIGS[args.config])
-    c.update(steps=args.steps, gbs=c["lbs"] * world * args.grad_accum, attn=args.attn)
+    c.update(steps=args.steps, gbs=c["lbs"] * world * args.grad_accum, attn=args.attn, dtype=args.dtype)
     y = YAML.format(**c)
     if args.strategy == "b200_sharded":
         import automodel_b200.integration as b200
@@ -131,7 +136,7 @@ def run(args):
             eng = model.engine
             eng.sync_params()
             for name, dst in eng.P.items():
-                dst.copy_(det_init(name, dst.shape, dev).to(dst.dtype))
+                dst.copy_(det_init(name, dst.shape, dev).to(torch.bfloat16).to(dst.dtype))
             eng.refresh_master_()
             for t in eng.m + eng.v:
                 t.zero_()
@@ -145,13 +150,15 @@ def run(args):
             fn = _ru._compute_llama3_inv_freq if sc.get("rope_type", sc.get("type", "default")) == "llama3" else _ru._compute_default_inv_freq
             want = fn(model.config)[0].to(dev)
             inv_ok = bool(rot.inv_freq.device.type == "cuda" and torch.equal(rot.inv_freq.float(), want))
+            have = rot.inv_freq.float().to(dev)
+            globals()["_INV_DEV"] = float(((have - want).abs() / want.abs()).max()) if have.shape == want.shape else float("nan")
             if not inv_ok:
                 rot.inv_freq = want
                 rot._cos_cache = rot._sin_cache = None
                 rot.max_seq_len_cached = 0
             globals()["_INV_OK"] = inv_ok
             for name, p in model.named_parameters():
-                full = det_init(name, p.shape, dev).to(p.dtype)
+                full = det_init(name, p.shape, dev).to(torch.bfloat16).to(p.dtype)   # bf16-representable in every dtype
                 if isinstance(p, DTensor):
                     p.copy_(distribute_tensor(full, p.device_mesh, p.placements))
                 else:
@@ -160,7 +167,10 @@ def run(args):
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t_setup
 
-    rec = {"ref_inv_freq_was_initialised": globals().get("_INV_OK"), "loss": [], "grad_norm": [], "step_ms": [], "tps": [], "ids_crc": [], "num_label_tokens": [], "mem_gb": []}
+    if args.fwd_only:
+        return fwd_only(args, r, model, c, dev)
+
+    rec = {"ref_inv_freq_was_initialised": globals().get("_INV_OK"), "ref_inv_freq_max_rel_dev_from_formula": globals().get("_INV_DEV"), "loss": [], "grad_norm": [], "step_ms": [], "tps": [], "ids_crc": [], "num_label_tokens": [], "mem_gb": []}
     orig = r._run_train_optim_step
 
     def spy(batches, max_grad_norm=None):
@@ -211,7 +221,7 @@ def run(args):
         skip = min(5, max(0, len(rec["step_ms"]) - 1))
         ms = rec["step_ms"][skip:]
         rec.update({
-            "strategy": args.strategy, "config": args.config, "world": world, "grad_accum": args.grad_accum, "attn": args.attn, "loss_kind": args.loss,
+            "strategy": args.strategy, "config": args.config, "world": world, "grad_accum": args.grad_accum, "attn": args.attn, "sdpa_backend": args.sdpa_backend, "loss_kind": args.loss,
             "setup_s": setup_s, "mean_step_ms": sum(ms) / len(ms), "median_step_ms": sorted(ms)[len(ms) // 2], "skipped_steps": skip,
             "tokens_per_step": c["lbs"] * c["seq"] * world * args.grad_accum,
             "model_class": type(model).__name__, "optimizer_class": type(r.optimizer[0]).__name__, "loss_class": type(r.loss_fn).__name__,
@@ -228,6 +238,39 @@ def run(args):
     import torch.distributed as dist
     if dist.is_initialized():
         dist.barrier()
+        dist.destroy_process_group()
+
+
+def fwd_only(args, r, model, c, dev):
+    """Noise-floor experiment: the loss of the INITIAL weights on the first N batches of the recipe's data loader, forward only.  Run for the
+    reference in bf16, the reference in fp32 (same bf16-representable weights: the exact-arithmetic answer) and ours; the per-token NLLs
+    are saved so that |bf16 reference - fp32| and |ours - fp32| can be compared token by token."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    out = {"loss": [], "strategy": args.strategy, "dtype": args.dtype, "config": args.config}
+    nll_all = []
+    it = iter(r.dataloader)
+    model.eval()
+    with torch.no_grad():
+        for i in range(args.fwd_only):
+            batch = next(it)
+            ids = batch["input_ids"].to(dev)
+            labels = batch["labels"].to(dev)
+            o = model(input_ids=ids, position_ids=batch["position_ids"].to(dev))
+            logits = o.logits if hasattr(o, "logits") else o
+            nll = F.cross_entropy(logits.float().view(-1, logits.shape[-1]), labels.view(-1), ignore_index=-100, reduction="none")
+            n = int((labels != -100).sum())
+            out["loss"].append(float(nll.sum() / n))
+            nll_all.append(nll.cpu().numpy())
+            out.setdefault("ids_crc", []).append(zlib.crc32(batch["input_ids"].numpy().tobytes()))
+            del o, logits
+    os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+    json.dump(out, open(args.out, "w"))
+    np.savez_compressed(os.path.splitext(args.out)[0] + "_nll.npz", nll=np.stack(nll_all))
+    print(f"[{args.strategy} {args.dtype}] fwd-only losses: {[round(x, 5) for x in out['loss']]}", file=sys.stderr, flush=True)
+    import torch.distributed as dist
+    if dist.is_initialized():
         dist.destroy_process_group()
 
 
@@ -283,6 +326,38 @@ def compare(a_path, b_path, md=None):
     return 0 if ok else 1
 
 
+def noise(truth_p, ref_p, ours_p, md=None):
+    """Noise floor of the bf16 forward: per-token NLLs of the same weights on the same batches from (fp32 reference = exact arithmetic,
+    bf16 reference, ours)."""
+    import numpy as np
+    t, a, b = (np.load(os.path.splitext(p)[0] + "_nll.npz")["nll"].astype(np.float64) for p in (truth_p, ref_p, ours_p))
+    mask = t != 0
+    nb = t.shape[0]
+    lines = []
+    P = lines.append
+    P(f"### forward noise floor, initial weights, {nb} batches ({int(mask.sum() // nb)} label tokens each)")
+    P("")
+    P("| batch | fp32 reference loss | bf16 reference - fp32 | ours - fp32 | ours - bf16 reference |")
+    P("|---:|---:|---:|---:|---:|")
+    rows = []
+    for i in range(nb):
+        m = mask[i]
+        lt, la, lb = t[i][m].mean(), a[i][m].mean(), b[i][m].mean()
+        rows.append((la - lt, lb - lt, lb - la))
+        P(f"| {i} | {lt:.5f} | {la - lt:+.2e} | {lb - lt:+.2e} | {lb - la:+.2e} |")
+    r = np.array(rows)
+    P(f"| rms | | {np.sqrt((r[:, 0] ** 2).mean()):.2e} | {np.sqrt((r[:, 1] ** 2).mean()):.2e} | {np.sqrt((r[:, 2] ** 2).mean()):.2e} |")
+    P("")
+    P(f"* per-token |NLL - fp32|: bf16 reference rms {np.sqrt(((a - t)[mask] ** 2).mean()):.3e}, ours rms {np.sqrt(((b - t)[mask] ** 2).mean()):.3e}; "
+      f"ours vs bf16 reference rms {np.sqrt(((b - a)[mask] ** 2).mean()):.3e}")
+    text = "\n".join(lines)
+    print(text)
+    if md:
+        with open(md, "a") as f:
+            f.write(text + "\n\n")
+    return 0
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--strategy", default="fsdp2", choices=["fsdp2", "b200_sharded"])
@@ -292,10 +367,16 @@ if __name__ == "__main__":
     ap.add_argument("--attn", default="sdpa")
     ap.add_argument("--loss", default="reference", choices=["reference", "fused"])
     ap.add_argument("--reduce-dtype", default=None)
+    ap.add_argument("--sdpa-backend", default=None, choices=["flash", "cudnn", "efficient", "math"])
+    ap.add_argument("--dtype", default="bfloat16", help="torch_dtype of the reference model (float32: exact-arithmetic run of the same weights)")
+    ap.add_argument("--fwd-only", type=int, default=0, help="noise-floor mode: loss of the initial weights on N batches, no training")
     ap.add_argument("--out", default="gpurun_out/ref_run.json")
     ap.add_argument("--compare", nargs=2, default=None)
+    ap.add_argument("--noise", nargs=3, default=None, metavar=("FP32_REF", "BF16_REF", "OURS"))
     ap.add_argument("--md", default=None)
     a = ap.parse_args()
+    if a.noise:
+        sys.exit(noise(a.noise[0], a.noise[1], a.noise[2], a.md))
     if a.compare:
         sys.exit(compare(a.compare[0], a.compare[1], a.md))
     run(a)
