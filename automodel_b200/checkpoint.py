@@ -53,16 +53,40 @@ def load_model(engine, path_or_file):
 
 
 def load_checkpoint(engine, path):
-    """Resume: model + this rank's optimizer shards + step counter.  The shard layout must match (same world size)."""
+    """Resume: model + this rank's optimizer shards + step counter.  A checkpoint written at another world size is re-sharded: the flat
+    optimizer state of a unit is the concatenation of the old ranks' shards (minus the old padding), of which this rank takes its new
+    contiguous slice (the reference gets the same from DCP's resharding load, components/checkpoint/checkpointing.py:382-572)."""
+    from safetensors import safe_open
     meta = json.load(open(os.path.join(path, "b200_meta.json")))
-    if meta["world"] != engine.world:
-        raise ValueError(f"checkpoint was written with world size {meta['world']}, engine has {engine.world} (re-sharding optimizer state is not implemented)")
     load_model(engine, os.path.join(path, "model.safetensors"))
-    opt = load_file(os.path.join(path, f"optim_rank{engine.rank}.safetensors"))
+    old_world = int(meta["world"])
+    kinds = ["m", "v"] + (["master"] if engine.master is not None else [])
+    dst = {"m": engine.m, "v": engine.v, "master": engine.master}
+    if old_world == engine.world:
+        opt = load_file(os.path.join(path, f"optim_rank{engine.rank}.safetensors"))
+        with torch.no_grad():
+            for ui, u in enumerate(engine.units):
+                for k in kinds:
+                    dst[k][ui].copy_(opt[f"{k}.{u.name}"])
+        engine.step_count = int(opt["step_count"][0])
+        return
+    old_padded = {name: padded for name, _, padded in meta["units"]}
+    files = [safe_open(os.path.join(path, f"optim_rank{r}.safetensors"), framework="pt") for r in range(old_world)]
     with torch.no_grad():
         for ui, u in enumerate(engine.units):
-            engine.m[ui].copy_(opt[f"m.{u.name}"])
-            engine.v[ui].copy_(opt[f"v.{u.name}"])
-            if engine.master is not None:
-                engine.master[ui].copy_(opt[f"master.{u.name}"])
-    engine.step_count = int(opt["step_count"][0])
+            a, b = u.shard_range(engine.rank, engine.world)          # this rank's new slice of the unit's flat index space
+            per_old = old_padded[u.name] // old_world
+            for k in kinds:
+                key = f"{k}.{u.name}"
+                if key not in files[0].keys():
+                    raise KeyError(f"checkpoint has no {key} (written without fp32 master weights?)")
+                out = dst[k][ui]
+                out.zero_()                                          # elements beyond u.numel are padding
+                lo, hi = a, min(b, u.numel)
+                pos = lo
+                while pos < hi:
+                    r_old, off = divmod(pos, per_old)
+                    n = min(hi - pos, per_old - off)
+                    out[pos - a:pos - a + n].copy_(files[r_old].get_slice(key)[off:off + n])
+                    pos += n
+    engine.step_count = int(files[0].get_tensor("step_count")[0])

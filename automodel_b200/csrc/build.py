@@ -5,7 +5,7 @@ import sys
 import hashlib
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["gemm_tcgen05.cu", "gemm_tcgen05_2cta.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "attention_fwd64.cu", "comm.cu", "c_api.cu"]
+SOURCES = ["gemm_tcgen05.cu", "gemm_tcgen05_2cta.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "attention_fwd64.cu", "attention_fwd_ts.cu", "comm.cu", "c_api.cu"]
 HEADERS = ["ptx.cuh", "common.h", "../../include/b200_train.h"]
 LIB = os.path.join(HERE, "libb200_train.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -43,6 +43,20 @@ def check_collectives(eng: ShardedLlamaEngine, unit_index: int = 1, seed: int = 
     got = eng.g_full[ui][a:b]
     rs_ulp = _bf16_ulp_distance(got, want)
     rs_exact = float((got == want).float().mean().item())
+    # a few mismatching elements of rank 0's slice with every rank's addend (how does the reducing hardware round?)
+    per = (b - a)
+    idx = torch.nonzero(got != want).flatten()[:4] if eng.rank == 0 else torch.zeros(0, dtype=torch.int64, device=dev)
+    pick = torch.full((4,), -1, dtype=torch.int64, device=dev)
+    pick[:idx.numel()] = idx
+    dist.broadcast(pick, src=dist.get_global_rank(pg, 0), group=pg)
+    sel = pick.clamp_min(0)
+    addends = [torch.empty(4, dtype=torch.float32, device=dev) for _ in range(eng.world)]
+    dist.all_gather(addends, x[sel].float(), group=pg)            # rank 0's slice starts at element 0 of the unit
+    examples = []
+    if eng.rank == 0:
+        for k in range(4):
+            if int(pick[k]) >= 0:
+                examples.append({"addends": [float(t[k]) for t in addends], "fp32_sum": float(ref32[sel[k]]), "got": float(got[sel[k]]), "rne": float(want[sel[k]])})
     # the grad-norm partial that the reduce-scatter path accumulated for this shard
     norm_rel = abs(float(eng.norm_sq[0]) - float(got.float().pow(2).sum())) / max(float(got.float().pow(2).sum()), 1e-30)
     eng._rs_started = False
@@ -64,7 +78,7 @@ def check_collectives(eng: ShardedLlamaEngine, unit_index: int = 1, seed: int = 
     rs_ulp, inexact, norm_rel, ag_bad = stats.tolist()
     return {"unit_elems": int(n), "comm": eng.comm_kind, "reduce_dtype": "float32" if eng.sym is not None else eng.reduce_dtype,
             "rs_max_bf16_ulp_vs_fp32_allreduce": int(rs_ulp), "rs_frac_not_bit_equal": inexact, "rs_norm_sq_rel_err": norm_rel,
-            "ag_bit_exact": ag_bad == 0.0}
+            "ag_bit_exact": ag_bad == 0.0, "rs_mismatch_examples_rank0": examples}
 
 
 PARITY_CFG = {"vocab_size": 2048, "hidden_size": 512, "intermediate_size": 1024, "num_hidden_layers": 2, "num_attention_heads": 4,

@@ -1,11 +1,10 @@
-"""GPU checks of switches that are implemented but were not yet exercised on a B200.  Not part of the default `-m gpu`
-gate: run with B200_TEST_EXPERIMENTAL=1 (first GPU call of the next round), then move what passes into the regular suites."""
-import os
-
+"""GPU checks of the engine's optional schedules: activation checkpointing (reference: distributed.activation_checkpointing,
+components/distributed/parallelizer.py:222-286), the cluster-launch-control GEMM tile scheduler inside the step, the SwiGLU GEMM epilogue.
+First run green on a B200 in round 2 (gpurun_out/r2_experimental.log, 7 passed); part of the default `-m gpu` gate since."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("B200_TEST_EXPERIMENTAL") != "1", reason="set B200_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 from automodel_b200 import ops  # noqa: E402
 from automodel_b200.engine import ShardedLlamaEngine  # noqa: E402

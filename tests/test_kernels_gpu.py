@@ -268,7 +268,7 @@ def attn_impl(request):
 DEFAULT_FWD_VARIANT = 1
 
 
-@pytest.mark.parametrize("attn_impl", [(1, 0), (1, 1), (0, 0)], indirect=True, ids=["tcgen05", "tcgen05_fwd64", "mma_v1"])
+@pytest.mark.parametrize("attn_impl", [(1, 0), (1, 1), (1, 2), (0, 0)], indirect=True, ids=["tcgen05", "tcgen05_fwd64", "tcgen05_p_in_tmem", "mma_v1"])
 @pytest.mark.parametrize("D,Hq,Hkv", [(64, 4, 2), (128, 4, 1), (128, 2, 2)])
 @pytest.mark.parametrize("lens", [[512], [64], [1], [200, 57, 255], [130, 1, 64, 63, 65], [1024, 129, 127, 128, 300]])
 def test_attention_fwd_bwd(D, Hq, Hkv, lens, attn_impl):
