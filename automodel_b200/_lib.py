@@ -21,6 +21,9 @@ SIGNATURES = {
     "b200_rmsnorm_bwd_workspace_floats": (_i, [_i, _i]),
     "b200_rmsnorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
     "b200_rope_inplace": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b200_bias_rope_inplace": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b200_colsum_workspace_floats": (_i, [_i, _i]),
+    "b200_colsum_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i, _vp]),
     "b200_swiglu_fwd": (_i, [_vp, _vp, _i64, _i, _vp]),
     "b200_swiglu_bwd": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
     "b200_embed_fwd": (_i, [_vp, _vp, _vp, _i, _i, _vp]),

@@ -32,6 +32,30 @@ __device__ __forceinline__ float ex2a(float x) {
   return y;
 }
 
+// 2^x for x <= 0 on the FMA / integer pipes (two elements per call, packed): round-to-nearest split x = n + f with the 1.5*2^23 magic
+// constant, degree-3 minimax polynomial of 2^f on [-0.5, 0.5] (max relative error 7.5e-5, 1/27 of a bf16 half-ulp), n added into the
+// exponent field.  Takes MUFU.EX2 (16 results per clock per SM - exactly as many clocks per kv tile as the tile's MMAs) off the
+// critical resource for a fraction of the elements.
+__device__ __forceinline__ void ex2_poly2(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  f2_unpack(x2, x0, x1);
+  x0 = fmaxf(x0, -125.f);   // masked (-inf) and underflowing scores: a denormal-sized weight, i.e. zero at bf16 precision
+  x1 = fmaxf(x1, -125.f);
+  const uint64_t x = f2_pack(x0, x1);
+  const uint64_t magic = f2_pack(12582912.f, 12582912.f);
+  const uint64_t xr = f2_add(x, magic);                                  // low mantissa bits = round(x) (two's complement)
+  const uint64_t nf = f2_add(xr, f2_pack(-12582912.f, -12582912.f));     // round(x) as a float
+  const uint64_t f = f2_add(x, f2_mul(nf, f2_pack(-1.f, -1.f)));         // f in [-0.5, 0.5]
+  uint64_t p = f2_fma(f2_pack(0.0551716574f, 0.0551716574f), f, f2_pack(0.2426111251f, 0.2426111251f));
+  p = f2_fma(p, f, f2_pack(0.6932609677f, 0.6932609677f));
+  p = f2_fma(p, f, f2_pack(0.9999280572f, 0.9999280572f));
+  float a, b, r0, r1;
+  f2_unpack(p, a, b);
+  f2_unpack(xr, r0, r1);
+  p0 = __uint_as_float(__float_as_uint(a) + (__float_as_uint(r0) << 23));
+  p1 = __uint_as_float(__float_as_uint(b) + (__float_as_uint(r1) << 23));
+}
+
 template <int D>
 struct Smem {
   static constexpr int TILE_Q = 128 * D * 2;   // D/64 boxes of [128 rows x 64 cols]
@@ -44,7 +68,8 @@ struct Smem {
   static constexpr int DYN = BAR_OFF + NUM_BARS * 8 + 16;  // 98,424 B at D=128: two CTAs per SM
 };
 
-template <int D>
+// EMU: of every 8 consecutive kv columns, the first EMU (0, 2 or 4) take the polynomial path, the rest MUFU.EX2
+template <int D, int EMU>
 __global__ void __launch_bounds__(192, 2)
 attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    __nv_bfloat16* __restrict__ o, float* __restrict__ lse, const int* __restrict__ cu_seqlens, int64_t ldo, int Hq, int Hkv, int T,
@@ -180,12 +205,13 @@ attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             if (kv > qrow || kv >= len) v[c][e] = 0xff800000u;   // -inf
           }
       }
-      float mx = -INFINITY;   // row max of the raw scores (scale > 0: the max commutes with the scaling)
+      // row max of the raw scores (scale > 0: the max commutes with the scaling); four independent FMNMX3 chains of 8 instead of one of 32
+      float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) mx = fmax3(mx, __uint_as_float(v[c][e]), __uint_as_float(v[c][e + 1]));
-      mx *= scale_log2;
+        for (int e = 0; e < 32; e += 2) mxa[(e >> 1) & 3] = fmax3(mxa[(e >> 1) & 3], __uint_as_float(v[c][e]), __uint_as_float(v[c][e + 1]));
+      float mx = fmaxf(fmax3(mxa[0], mxa[1], mxa[2]), mxa[3]) * scale_log2;
       if (j == 0) {
         m_used = (mx == -INFINITY) ? 0.f : mx;
       } else {
@@ -216,20 +242,27 @@ attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       const uint64_t neg_m = f2_pack(-m_used, -m_used);
       uint32_t pk[32];
-      uint64_t sum2 = f2_pack(0.f, 0.f);
+      uint64_t sum2[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          float x0, x1;
-          f2_unpack(f2_fma(f2_pack(__uint_as_float(v[c][e]), __uint_as_float(v[c][e + 1])), scale2, neg_m), x0, x1);
-          const float p0 = ex2a(x0), p1 = ex2a(x1);
-          sum2 = f2_add(sum2, f2_pack(p0, p1));
+          const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(v[c][e]), __uint_as_float(v[c][e + 1])), scale2, neg_m);
+          float p0, p1;
+          if ((e & 7) < EMU) {
+            ex2_poly2(x2, p0, p1);
+          } else {
+            float x0, x1;
+            f2_unpack(x2, x0, x1);
+            p0 = ex2a(x0);
+            p1 = ex2a(x1);
+          }
+          sum2[(e >> 1) & 1] = f2_add(sum2[(e >> 1) & 1], f2_pack(p0, p1));
           pk[c * 16 + (e >> 1)] = pack_bf16x2(p0, p1);
         }
       }
       float sa, sb;
-      f2_unpack(sum2, sa, sb);
+      f2_unpack(f2_add(sum2[0], sum2[1]), sa, sb);
       l_sum += sa + sb;
       // P_j (32 columns of bf16 pairs) over the first half of S_j: this thread has read its whole row of S_j above
       tmem_st_32x32b_x32(tS0 + lane_addr + st * 64, pk);
@@ -270,11 +303,11 @@ attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-template <int D>
+template <int D, int EMU>
 static int launch(const void* q, const void* k, const void* v, void* o, float* lse, const int* cu, int nseq, int max_len, int64_t ldq, int64_t ldk,
                   int64_t ldv, int64_t ldo, int Hq, int Hkv, int T, float scale, cudaStream_t st) {
   using L = Smem<D>;
-  auto kern = attn_fwd_ts_kernel<D>;
+  auto kern = attn_fwd_ts_kernel<D, EMU>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN);
@@ -294,13 +327,24 @@ static int launch(const void* q, const void* k, const void* v, void* o, float* l
 
 }  // namespace fwdts
 
+// emu: 0, 2 or 4 of every 8 exponentials on the FMA pipe (A/B knob; the default is chosen in c_api.cu)
 int attn_fwd_ts(const void* q, const void* k, const void* v, void* o, float* lse, const int* cu_seqlens, int nseq, int max_len, int64_t ldq,
-                int64_t ldk, int64_t ldv, int64_t ldo, int Hq, int Hkv, int D, int T, float scale, cudaStream_t st) {
+                int64_t ldk, int64_t ldv, int64_t ldo, int Hq, int Hkv, int D, int T, float scale, int emu, cudaStream_t st) {
   if (Hq % Hkv) return set_error(B200_ERR_ARG, "attn: Hq %% Hkv != 0");
   if ((ldq | ldk | ldv | ldo) % 8) return set_error(B200_ERR_ARG, "attn: row pitches must be multiples of 8 elements");
   if (scale <= 0.f) return set_error(B200_ERR_ARG, "attn: scale must be positive");
-  if (D == 128) return fwdts::launch<128>(q, k, v, o, lse, cu_seqlens, nseq, max_len, ldq, ldk, ldv, ldo, Hq, Hkv, T, scale, st);
-  if (D == 64) return fwdts::launch<64>(q, k, v, o, lse, cu_seqlens, nseq, max_len, ldq, ldk, ldv, ldo, Hq, Hkv, T, scale, st);
+#define B200_FWDTS(DD, EE) return fwdts::launch<DD, EE>(q, k, v, o, lse, cu_seqlens, nseq, max_len, ldq, ldk, ldv, ldo, Hq, Hkv, T, scale, st)
+  if (D == 128) {
+    if (emu == 4) B200_FWDTS(128, 4);
+    if (emu == 2) B200_FWDTS(128, 2);
+    B200_FWDTS(128, 0);
+  }
+  if (D == 64) {
+    if (emu == 4) B200_FWDTS(64, 4);
+    if (emu == 2) B200_FWDTS(64, 2);
+    B200_FWDTS(64, 0);
+  }
+#undef B200_FWDTS
   return set_error(B200_ERR_UNSUPPORTED, "attn: head_dim %d not in {64,128}", D);
 }
 

@@ -26,6 +26,9 @@ int rmsnorm_fwd(const void*, const void*, void*, float*, int, int, float, cudaSt
 int rmsnorm_bwd_workspace_floats(int, int);
 int rmsnorm_bwd(const void*, const void*, const void*, const float*, const void*, void*, void*, int, float*, int, int, cudaStream_t);
 int rope_inplace(void*, const void*, const void*, const int*, int, int, int, int, int, cudaStream_t);
+int bias_rope_inplace(void*, const void*, const void*, const void*, const int*, int, int, int, int, int, cudaStream_t);
+int colsum_workspace_floats(int, int);
+int colsum_bf16(const void*, void*, float*, int, int, int64_t, int, cudaStream_t);
 int swiglu_fwd(const void*, void*, int64_t, int, cudaStream_t);
 int swiglu_bwd(const void*, const void*, void*, int64_t, int, cudaStream_t);
 int embed_fwd(const int*, const void*, void*, int, int, cudaStream_t);
@@ -60,8 +63,8 @@ int allgather_layer(CommCtx*, int, size_t, int64_t, int, int, cudaStream_t);
 int attn_fwd_tc64(const void*, const void*, const void*, void*, float*, const int*, int, int, int64_t, int64_t, int64_t, int64_t, int, int,
                   int, int, float, cudaStream_t);
 int attn_fwd_ts(const void*, const void*, const void*, void*, float*, const int*, int, int, int64_t, int64_t, int64_t, int64_t, int, int,
-                int, int, float, cudaStream_t);
-static int g_attn_fwd_variant = 1;  // 1 (default): 64-row kv tiles, two CTAs per SM (attention_fwd64.cu, 622 vs 510 TFLOP/s); 0: attention_tc.cu forward
+                int, int, float, int, cudaStream_t);
+static int g_attn_fwd_variant = 2;  // 2 (default): P kept in tensor memory, packed-fp32 softmax (attention_fwd_ts.cu, 902 TFLOP/s); 1: attention_fwd64.cu (624); 0: attention_tc.cu forward (510); 3 / 4: variant 2 with 2 / 4 of every 8 exponentials on the FMA pipe (861 / 816: MUFU is not the limiter)
 
 // debug option: 1 (default) = tcgen05/TMEM attention, 0 = the mma.sync v1 kernels (kept for bisecting only)
 static int g_attn_impl = 1;
@@ -172,6 +175,14 @@ int b200_rope_inplace(void* qk, const void* cos_table, const void* sin_table, co
                       int head_dim, int ld, int backward, b200_stream_t stream) {
   return rope_inplace(qk, cos_table, sin_table, position_ids, tokens, heads, head_dim, ld, backward, S(stream));
 }
+int b200_bias_rope_inplace(void* qkv, const void* bias, const void* cos_table, const void* sin_table, const int* position_ids, int tokens,
+                           int rope_heads, int heads, int head_dim, int ld, b200_stream_t stream) {
+  return bias_rope_inplace(qkv, bias, cos_table, sin_table, position_ids, tokens, rope_heads, heads, head_dim, ld, S(stream));
+}
+int b200_colsum_workspace_floats(int rows, int cols) { return colsum_workspace_floats(rows, cols); }
+int b200_colsum_bf16(const void* x, void* out, float* workspace, int rows, int cols, int64_t ld, int accumulate, b200_stream_t stream) {
+  return colsum_bf16(x, out, workspace, rows, cols, ld, accumulate, S(stream));
+}
 int b200_swiglu_fwd(const void* gu, void* a, int64_t tokens, int ffn, b200_stream_t stream) { return swiglu_fwd(gu, a, tokens, ffn, S(stream)); }
 int b200_swiglu_bwd(const void* da, const void* gu, void* dgu, int64_t tokens, int ffn, b200_stream_t stream) {
   return swiglu_bwd(da, gu, dgu, tokens, ffn, S(stream));
@@ -185,8 +196,9 @@ int b200_embed_bwd(const int* ids, const void* dh, void* dW, int* workspace, int
 int b200_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const int* cu_seqlens, int nseq, int max_seqlen,
                   int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int Hq, int Hkv, int head_dim, int total_tokens, float scale,
                   b200_stream_t stream) {
-  if (g_attn_impl == 1 && g_attn_fwd_variant == 2)
-    return attn_fwd_ts(q, k, v, o, lse, cu_seqlens, nseq, max_seqlen, ldq, ldk, ldv, ldo, Hq, Hkv, head_dim, total_tokens, scale, S(stream));
+  if (g_attn_impl == 1 && g_attn_fwd_variant >= 2)   // 2: every exponential on MUFU; 3 / 4: 2 / 4 of every 8 on the FMA pipe (polynomial)
+    return attn_fwd_ts(q, k, v, o, lse, cu_seqlens, nseq, max_seqlen, ldq, ldk, ldv, ldo, Hq, Hkv, head_dim, total_tokens, scale,
+                       g_attn_fwd_variant == 2 ? 0 : (g_attn_fwd_variant == 3 ? 2 : 4), S(stream));
   if (g_attn_impl == 1 && g_attn_fwd_variant == 1)
     return attn_fwd_tc64(q, k, v, o, lse, cu_seqlens, nseq, max_seqlen, ldq, ldk, ldv, ldo, Hq, Hkv, head_dim, total_tokens, scale, S(stream));
   if (g_attn_impl == 1)

@@ -377,6 +377,125 @@ int rope_inplace(void* qk, const void* cos_t, const void* sin_t, const int* pos,
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------- qkv bias (+ RoPE) and its gradient
+// Qwen2 attention (components/models/qwen2/model.py:80-82: q/k/v projections with bias=True).  Forward: ONE in-place pass over the fused
+// qkv row that adds the bias to every head and rotates the first `rope_heads` heads (q and k) - the pass the bias-free path spends on
+// RoPE alone, so the bias costs no extra HBM traffic.  y = bf16(bf16(x) + b) then the rotate-half RoPE of rope_kernel.
+__global__ void __launch_bounds__(320, 4) bias_rope_kernel(__nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ bias,
+                                                       const __nv_bfloat16* __restrict__ cos_t, const __nv_bfloat16* __restrict__ sin_t,
+                                                       const int* __restrict__ pos, int rope_heads, int heads, int head_dim, int ld) {
+  const int cpr = head_dim / 16;  // 16B chunks per half head
+  const int items = heads * cpr;
+  const int t = blockIdx.x;
+  const int p = pos[t];
+  __nv_bfloat16* row = qkv + static_cast<size_t>(t) * ld;
+  const __nv_bfloat16* ct = cos_t + static_cast<size_t>(p) * head_dim;
+  const __nv_bfloat16* st = sin_t + static_cast<size_t>(p) * head_dim;
+  for (int w = threadIdx.x; w < items; w += blockDim.x) {
+    const int h = w / cpr;
+    const int c = w - h * cpr;
+    const int col = h * head_dim + c * 8;
+    __nv_bfloat16* base = row + col;
+    float x1[8], x2[8], b1[8], b2[8];
+    unpack8(*reinterpret_cast<const uint4*>(base), x1);
+    unpack8(*reinterpret_cast<const uint4*>(base + head_dim / 2), x2);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(bias + col)), b1);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(bias + col + head_dim / 2)), b2);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      x1[e] = bf16_round(x1[e] + b1[e]);
+      x2[e] = bf16_round(x2[e] + b2[e]);
+    }
+    if (h < rope_heads) {
+      float c1[8], s1[8], c2[8], s2[8], o1[8], o2[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(ct + c * 8)), c1);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(st + c * 8)), s1);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(ct + c * 8 + head_dim / 2)), c2);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(st + c * 8 + head_dim / 2)), s2);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {   // out1 = x1*cos - x2*sin ; out2 = x2*cos + x1*sin, each product a materialised bf16 tensor
+        o1[e] = bf16_round(x1[e] * c1[e]) - bf16_round(x2[e] * s1[e]);
+        o2[e] = bf16_round(x2[e] * c2[e]) + bf16_round(x1[e] * s2[e]);
+      }
+      *reinterpret_cast<uint4*>(base) = pack8(o1);
+      *reinterpret_cast<uint4*>(base + head_dim / 2) = pack8(o2);
+    } else {
+      *reinterpret_cast<uint4*>(base) = pack8(x1);
+      *reinterpret_cast<uint4*>(base + head_dim / 2) = pack8(x2);
+    }
+  }
+}
+
+int bias_rope_inplace(void* qkv, const void* bias, const void* cos_t, const void* sin_t, const int* pos, int tokens, int rope_heads, int heads,
+                      int head_dim, int ld, cudaStream_t st) {
+  if (head_dim % 16 != 0 || ld % 8 != 0) return set_error(B200_ERR_ARG, "bias_rope: head_dim %% 16 and ld %% 8 required");
+  if (rope_heads < 0 || rope_heads > heads) return set_error(B200_ERR_ARG, "bias_rope: rope_heads %d outside 0..%d", rope_heads, heads);
+  if (tokens <= 0 || heads <= 0) return 0;
+  const int items = heads * (head_dim / 16);
+  int threads = (items + 31) / 32 * 32;
+  if (threads > 320) threads = 320;
+  bias_rope_kernel<<<tokens, threads, 0, st>>>(static_cast<__nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(bias),
+                                               static_cast<const __nv_bfloat16*>(cos_t), static_cast<const __nv_bfloat16*>(sin_t), pos, rope_heads,
+                                               heads, head_dim, ld);
+  B200_CHECK_LAUNCH("bias_rope");
+  return 0;
+}
+
+// Column sums of a bf16 [rows, cols] matrix (row pitch ld): the bias gradient db = sum_t dy[t, :] (autograd of nn.Linear's bias: fp32
+// accumulation, one rounding).  Two deterministic stages: CTA (x, y) sums rows y, y + gridDim.y, ... of a 256-column strip into
+// partial[y][cols]; the finalize kernel adds the partials in a fixed order and writes / accumulates the bf16 result.
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial, int rows, int cols,
+                                                            int64_t ld) {
+  const int c8 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 8;   // 32 lanes x 8 columns = one 256-column strip per CTA
+  const int rsub = threadIdx.x >> 5;                            // 8 row phases inside the CTA
+  __shared__ float s_acc[8][256];
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c8 < cols) {
+    for (int r = blockIdx.y * 8 + rsub; r < rows; r += gridDim.y * 8) {
+      float f[8];
+      unpack8(ld_stream(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r) * ld + c8)), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s_acc[rsub][(threadIdx.x & 31) * 8 + e] = acc[e];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s_acc[i][threadIdx.x];
+    partial[static_cast<int64_t>(blockIdx.y) * cols + c] = t;
+  }
+}
+__global__ void __launch_bounds__(256) colsum_finalize_kernel(const float* __restrict__ partial, int nparts, int cols, __nv_bfloat16* __restrict__ out,
+                                                             int accumulate) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= cols) return;
+  float t = 0.f;
+  for (int i = 0; i < nparts; ++i) t += partial[static_cast<int64_t>(i) * cols + c];
+  if (accumulate) t = bf16_round(t) + __bfloat162float(out[c]);   // micro-batch accumulation: += of materialised bf16 gradients
+  out[c] = __float2bfloat16_rn(t);
+}
+
+static int colsum_parts(int rows) {
+  int p = (rows + 63) / 64;
+  return p < 1 ? 1 : (p > 64 ? 64 : p);
+}
+int colsum_workspace_floats(int rows, int cols) { return colsum_parts(rows) * cols; }
+int colsum_bf16(const void* x, void* out, float* ws, int rows, int cols, int64_t ld, int accumulate, cudaStream_t st) {
+  if (cols % 8 || ld % 8) return set_error(B200_ERR_ARG, "colsum: cols %% 8 and ld %% 8 required");
+  if (rows <= 0 || cols <= 0) return 0;
+  const int parts = colsum_parts(rows);
+  dim3 grid((cols + 255) / 256, parts);
+  colsum_partial_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ws, rows, cols, ld);
+  B200_CHECK_LAUNCH("colsum_partial");
+  colsum_finalize_kernel<<<(cols + 255) / 256, 256, 0, st>>>(ws, parts, cols, static_cast<__nv_bfloat16*>(out), accumulate);
+  B200_CHECK_LAUNCH("colsum_finalize");
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------- SwiGLU
 // gu [T, 2F]: gate = cols [0,F), up = cols [F,2F).   a = bf16(bf16(silu(g)) * u)
 __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ a,

@@ -296,6 +296,13 @@ class ShardedLlamaEngine:
                 "d_n1": gf[off["input_layernorm.weight"]:off["input_layernorm.weight"] + d.hidden],
                 "d_n2": gf[off["post_attention_layernorm.weight"]:off["post_attention_layernorm.weight"] + d.hidden],
             })
+            if d.qkv_bias:
+                ob = off["self_attn.q_proj.bias"]
+                self.W[-1]["qkv_b"] = pf[ob:ob + d.qkv_cols]
+                self.W[-1]["d_qkv_b"] = gf[ob:ob + d.qkv_cols]
+        # lm_head matrix and its gradient: the embed unit's when the embeddings are tied
+        head = "model.embed_tokens.weight" if d.tied else "lm_head.weight"
+        self.lm_head_w, self.lm_head_g = self.P[head], self.G[head]
 
     def load_state_dict(self, sd):
         """sd: HF-named full tensors (torch or numpy, any float dtype).  Every rank loads the full model (the metric's
@@ -367,6 +374,8 @@ class ShardedLlamaEngine:
             for name, p in self.P.items():
                 if name.endswith("norm.weight") or "layernorm" in name:
                     p.fill_(1.0)
+                elif name.endswith(".bias"):
+                    p.zero_()
                 else:
                     p.copy_((torch.randn(p.shape, generator=g, device=self.device, dtype=torch.float32) * std).to(p.dtype))
         self.load_state_dict(self.P)
@@ -657,7 +666,7 @@ class ShardedLlamaEngine:
         xf = sl(self.xf)
         ops.rmsnorm_fwd(hL, self.P["model.norm.weight"], d.eps, out=xf, rstd=sl(self.rstdf))
         logits = sl(self.logits)
-        G(ops.NT, xf, self.P["lm_head.weight"], out=logits)
+        G(ops.NT, xf, self.lm_head_w, out=logits)
         return logits
 
     def _layer_forward(self, l, T, pos, cu, max_len):
@@ -679,7 +688,10 @@ class ShardedLlamaEngine:
         x2 = sl(A["x2"][l]); gu = sl(A["gu"][l]); a = sl(A["a"][l])
         ops.rmsnorm_fwd(h, W["n1"], d.eps, out=x1, rstd=sl(A["rstd1"][l]))
         G(ops.NT, x1, W["qkv"], out=qkv)
-        ops.rope_(qkv, self.cos, self.sin, pos, Hq + Hkv, D)
+        if d.qkv_bias:
+            ops.bias_rope_(qkv, W["qkv_b"], self.cos, self.sin, pos, Hq + Hkv, Hq + 2 * Hkv, D)
+        else:
+            ops.rope_(qkv, self.cos, self.sin, pos, Hq + Hkv, D)
         ops.attn_fwd(qkv[:, :qc], qkv[:, qc:qc + kc], qkv[:, qc + kc:], cu, max_len, Hq, Hkv, D, out=o2, lse=A["lse"][l])
         G(ops.NT, o2, W["o"], out=h1, residual=h, round_before_add=rba)
         ops.rmsnorm_fwd(h1, W["n2"], d.eps, out=x2, rstd=sl(A["rstd2"][l]))
@@ -735,9 +747,10 @@ class ShardedLlamaEngine:
                 st.wait(self.ev_opt_all, st.wg)
             self.ev_opt_all = None
         head_ui = 1 + L
-        WG((), logits, xf, self.G["lm_head.weight"])
+        WG((), logits, xf, self.lm_head_g)
+        head_wg = self._wg_last if self._wg_on else None   # tied embeddings: the scatter-add at the end of backward accumulates on top of it
         dxf = sl(tmp["dxf"])
-        G(ops.NN, logits, self.P["lm_head.weight"], out=dxf)
+        G(ops.NN, logits, self.lm_head_w, out=dxf)
         dh = sl(tmp["dh_a"]); dh_next = sl(tmp["dh_b"])
         dh_name, dh_next_name = "dh_a", "dh_b"
         ops.rmsnorm_bwd(dxf, hL, self.P["model.norm.weight"], sl(self.rstdf), dx=dh, dw=self.G["model.norm.weight"],
@@ -774,6 +787,8 @@ class ShardedLlamaEngine:
             ops.attn_bwd(qkv[:, :qc], qkv[:, qc:qc + kc], qkv[:, qc + kc:], o2, do2, A["lse"][l], cu, max_len, Hq, Hkv, D,
                          dqkv[:, :qc], dqkv[:, qc:qc + kc], dqkv[:, qc + kc:], workspace=self.attn_ws)
             ops.rope_(dqkv, self.cos, self.sin, pos, Hq + Hkv, D, backward=True)
+            if d.qkv_bias:
+                ops.colsum_(dqkv, W["d_qkv_b"], accumulate=acc)
             WG(("dqkv",), dqkv, x1, W["d_qkv"])
             G(ops.NN, dqkv, W["qkv"], out=dx)
             before_write(dh_next_name)
@@ -782,7 +797,9 @@ class ShardedLlamaEngine:
             dh_name, dh_next_name = dh_next_name, dh_name
             if last_micro:
                 self._reduce_scatter_unit(1 + l)
-        if first_micro:
+        if d.tied:
+            st.wait(head_wg)       # the lm_head weight gradient (= or += above) is in the shared matrix; the token rows add to it
+        elif first_micro:
             self.G["model.embed_tokens.weight"].zero_()
         ops.embed_bwd(ids, dh, self.G["model.embed_tokens.weight"], accumulate=True, workspace=self.embed_ws)
         if last_micro:

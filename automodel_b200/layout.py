@@ -28,6 +28,8 @@ class LlamaDims:
     rope_theta: float = 10000.0
     rope_scaling: dict = None
     max_pos: int = 4096
+    qkv_bias: bool = False        # Qwen2: q/k/v projections carry a bias (components/models/qwen2/model.py:80-82)
+    tied: bool = False            # tie_word_embeddings: lm_head shares model.embed_tokens.weight (Qwen2 <= 1.5B, Llama-3.2-1B/3B)
 
     @staticmethod
     def from_hf(cfg) -> "LlamaDims":
@@ -35,18 +37,23 @@ class LlamaDims:
         heads = g("num_attention_heads")
         hidden = g("hidden_size")
         mt = g("model_type")
-        if mt not in (None, "llama", "mistral"):
-            raise ValueError(f"model_type {mt!r}: the B200 sharded step implements the Llama decoder (llama, and mistral without sliding window)")
-        if g("sliding_window"):
+        if mt not in (None, "llama", "mistral", "qwen2"):
+            raise ValueError(f"model_type {mt!r}: the B200 sharded step implements the Llama-family decoder (llama, qwen2, and mistral without "
+                             "sliding window)")
+        if mt == "qwen2":
+            # Qwen2Config always carries a sliding_window size; it only applies when use_sliding_window is set (layer_types "sliding_attention")
+            if g("use_sliding_window", False) or any(t != "full_attention" for t in (g("layer_types") or [])):
+                raise ValueError("sliding-window attention is not supported")
+        elif g("sliding_window"):
             raise ValueError("sliding-window attention is not supported")
         if g("hidden_act", "silu") not in (None, "silu"):
             raise ValueError(f"hidden_act {g('hidden_act')!r}: the MLP kernels implement SwiGLU (silu) only")
         if (g("attention_dropout", 0.0) or 0.0) != 0.0:
             raise ValueError("attention_dropout != 0 is not supported")
-        if g("tie_word_embeddings", False):
-            raise ValueError("tie_word_embeddings=True is not supported by the B200 flat layout (Llama-3 is untied)")
-        if g("attention_bias", False) or g("mlp_bias", False):
-            raise ValueError("attention_bias / mlp_bias are not supported")
+        if g("mlp_bias", False):
+            raise ValueError("mlp_bias is not supported")
+        if mt != "qwen2" and g("attention_bias", False):
+            raise ValueError("attention_bias (bias on q/k/v AND o_proj) is not supported; Qwen2's q/k/v-only bias is")
         # RoPE base and scaling as the reference resolves them (components/models/llama/rope_utils.py:90-109): transformers >= 5 keeps both
         # in `rope_parameters` ({"rope_theta", "rope_type", "factor", ...}); older configs have `rope_theta` + `rope_scaling`.
         rp = g("rope_parameters")
@@ -59,7 +66,8 @@ class LlamaDims:
         return LlamaDims(hidden=hidden, ffn=g("intermediate_size"), layers=g("num_hidden_layers"), heads=heads,
                          kv_heads=g("num_key_value_heads") or heads, head_dim=g("head_dim") or hidden // heads,
                          vocab=g("vocab_size"), eps=g("rms_norm_eps", 1e-5), rope_theta=theta,
-                         rope_scaling=scaling, max_pos=g("max_position_embeddings", 4096))
+                         rope_scaling=scaling, max_pos=g("max_position_embeddings", 4096), qkv_bias=(mt == "qwen2"),
+                         tied=bool(g("tie_word_embeddings", False)))
 
     @property
     def q_cols(self):
@@ -130,8 +138,10 @@ def build_layout(d: LlamaDims, world: int) -> List[UnitLayout]:
             (p + "mlp.down_proj.weight", (d.hidden, d.ffn)),
             (p + "input_layernorm.weight", (d.hidden,)),
             (p + "post_attention_layernorm.weight", (d.hidden,)),
-        ], world))
-    units.append(_mk_unit("head", [("model.norm.weight", (d.hidden,)), ("lm_head.weight", (d.vocab, d.hidden))], world))
+        ] + ([(p + "self_attn.q_proj.bias", (d.q_cols,)), (p + "self_attn.k_proj.bias", (d.kv_cols,)), (p + "self_attn.v_proj.bias", (d.kv_cols,))]
+             if d.qkv_bias else []), world))     # q;k;v biases contiguous: one fused [(Hq+2Hkv)*d] vector
+    # tied embeddings: the head unit is the final norm alone; the lm_head GEMMs read / write the embed unit's matrix and gradient
+    units.append(_mk_unit("head", [("model.norm.weight", (d.hidden,))] + ([] if d.tied else [("lm_head.weight", (d.vocab, d.hidden))]), world))
     return units
 
 

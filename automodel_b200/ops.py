@@ -169,6 +169,31 @@ def rope_(qk, cos, sin, pos, heads, head_dim, backward=False):
     return qk
 
 
+def bias_rope_(qkv, bias, cos, sin, pos, rope_heads, heads, head_dim):
+    """In place on qkv [T, heads*head_dim]: += bias on every head, RoPE on the first `rope_heads` heads (Qwen2 q/k/v bias)."""
+    assert qkv.dtype == torch.bfloat16 and qkv.stride(1) == 1 and pos.dtype == torch.int32 and bias.numel() == heads * head_dim
+    check(lib().b200_bias_rope_inplace(qkv.data_ptr(), bias.data_ptr(), cos.data_ptr(), sin.data_ptr(), pos.data_ptr(), qkv.shape[0], rope_heads,
+                                       heads, head_dim, qkv.stride(0), _st()), "b200_bias_rope_inplace")
+    _count(1)
+    return qkv
+
+
+_cs_ws = {}
+
+
+def colsum_(x, out, accumulate=False):
+    """out[c] (=|+=) bf16(sum_t x[t, c]) with fp32 accumulation: the bias gradient."""
+    T, C = x.shape
+    assert x.stride(1) == 1 and out.numel() == C
+    need = lib().b200_colsum_workspace_floats(T, C)
+    ws = _cs_ws.get(x.device)
+    if ws is None or ws.numel() < need:
+        ws = _cs_ws[x.device] = torch.empty(need, dtype=torch.float32, device=x.device)
+    check(lib().b200_colsum_bf16(x.data_ptr(), out.data_ptr(), ws.data_ptr(), T, C, x.stride(0), int(accumulate), _st()), "b200_colsum_bf16")
+    _count(2)
+    return out
+
+
 def swiglu_fwd(gu, out=None):
     T, F2 = gu.shape
     assert gu.is_contiguous()

@@ -72,6 +72,15 @@ int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* 
 int b200_rope_inplace(void* qk, const void* cos_table, const void* sin_table, const int* position_ids, int tokens, int heads,
                       int head_dim, int ld, int backward, b200_stream_t stream);
 
+/* ---- qkv projection bias (Qwen2: components/models/qwen2/model.py:80-82, nn.Linear(bias=True) for q/k/v)
+ * forward: in place on the fused [tokens, heads*head_dim] qkv rows: y = bf16(x + bias) for every head, then RoPE (as b200_rope_inplace)
+ * on the first rope_heads heads (q and k).  backward: b200_rope_inplace(backward=1) on dq/dk as without bias, then the bias gradient is
+ * the column sum of dqkv: out[c] (=|+=) bf16(sum_t x[t, c]) with fp32 accumulation (deterministic two-stage reduction). */
+int b200_bias_rope_inplace(void* qkv, const void* bias, const void* cos_table, const void* sin_table, const int* position_ids, int tokens,
+                           int rope_heads, int heads, int head_dim, int ld, b200_stream_t stream);
+int b200_colsum_workspace_floats(int rows, int cols);
+int b200_colsum_bf16(const void* x, void* out, float* workspace, int rows, int cols, int64_t ld, int accumulate, b200_stream_t stream);
+
 /* ---- SwiGLU (components/models/llama/model.py:170); gu = [gate | up] columns */
 int b200_swiglu_fwd(const void* gu, void* a, int64_t tokens, int ffn, b200_stream_t stream);
 int b200_swiglu_bwd(const void* da, const void* gu, void* dgu, int64_t tokens, int ffn, b200_stream_t stream);

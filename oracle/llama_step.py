@@ -185,15 +185,21 @@ def _mm(a, b):
     return a @ b
 
 
-def linear_fwd(x, w, P):
-    """nn.Linear without bias: y = x W^T (W [out,in], HF layout)."""
-    return P.r(_mm(x, w.T))
+def linear_fwd(x, w, P, b=None):
+    """nn.Linear: y = x W^T (+ b) (W [out,in], HF layout).  With a bias (Qwen2 q/k/v, components/models/qwen2/model.py:80-82) the add
+    happens before the one down-cast (addmm)."""
+    y = _mm(x, w.T)
+    return P.r(y if b is None else y + b)
 
 
 def linear_bwd(dy, x, w, P):
     dx = P.r(_mm(dy, w))
     dw = P.r(_mm(dy.reshape(-1, dy.shape[-1]).T, x.reshape(-1, x.shape[-1])))
     return dx, dw
+
+
+def bias_bwd(dy, P):
+    return P.r(dy.reshape(-1, dy.shape[-1]).sum(0))
 
 
 def segments_from_position_ids(position_ids):
@@ -235,9 +241,9 @@ def forward_backward(params, cfg, input_ids, labels, num_label_tokens, prec="fp3
     for l in range(L):
         p = f"model.layers.{l}."
         x1, r1 = rmsnorm_fwd(h, W[p + "input_layernorm.weight"], eps, P)
-        q = linear_fwd(x1, W[p + "self_attn.q_proj.weight"], P).reshape(b, S, H, d).transpose(0, 2, 1, 3)
-        k = linear_fwd(x1, W[p + "self_attn.k_proj.weight"], P).reshape(b, S, Hkv, d).transpose(0, 2, 1, 3)
-        v = linear_fwd(x1, W[p + "self_attn.v_proj.weight"], P).reshape(b, S, Hkv, d).transpose(0, 2, 1, 3)
+        q = linear_fwd(x1, W[p + "self_attn.q_proj.weight"], P, W.get(p + "self_attn.q_proj.bias")).reshape(b, S, H, d).transpose(0, 2, 1, 3)
+        k = linear_fwd(x1, W[p + "self_attn.k_proj.weight"], P, W.get(p + "self_attn.k_proj.bias")).reshape(b, S, Hkv, d).transpose(0, 2, 1, 3)
+        v = linear_fwd(x1, W[p + "self_attn.v_proj.weight"], P, W.get(p + "self_attn.v_proj.bias")).reshape(b, S, Hkv, d).transpose(0, 2, 1, 3)
         qr, kr = rope_fwd(q, cos, sin, P), rope_fwd(k, cos, sin, P)
         o, pr = attention_fwd(qr, kr, v, scale, seg, P)
         o2 = o.transpose(0, 2, 1, 3).reshape(b, S, H * d)
@@ -250,7 +256,8 @@ def forward_backward(params, cfg, input_ids, labels, num_label_tokens, prec="fp3
         saved.append((h, x1, r1, qr, kr, v, pr, o2, h1, x2, r2, g, u, a))
         h = h2
     xf, rf = rmsnorm_fwd(h, W["model.norm.weight"], eps, P)
-    logits = linear_fwd(xf, W["lm_head.weight"], P)
+    head = "lm_head.weight" if "lm_head.weight" in W else "model.embed_tokens.weight"    # tie_word_embeddings: one shared matrix
+    logits = linear_fwd(xf, W[head], P)
     loss, dlogits = masked_ce_fwd_bwd(logits, labels, num_label_tokens, P)
     if not compute_grads:
         return loss, logits
@@ -262,8 +269,8 @@ def forward_backward(params, cfg, input_ids, labels, num_label_tokens, prec="fp3
     def acc(name, g_):
         grads[name] = P.r(grads[name] + g_) if name in grads else g_
 
-    dxf, dw = linear_bwd(dlogits, xf, W["lm_head.weight"], P)
-    acc("lm_head.weight", dw)
+    dxf, dw = linear_bwd(dlogits, xf, W[head], P)
+    acc(head, dw)
     dh, dw = rmsnorm_bwd(dxf, h, W["model.norm.weight"], rf, P)
     acc("model.norm.weight", dw)
     for l in reversed(range(L)):
@@ -294,6 +301,10 @@ def forward_backward(params, cfg, input_ids, labels, num_label_tokens, prec="fp3
         acc(p + "self_attn.k_proj.weight", dw)
         dx1v, dw = linear_bwd(dv2, x1, W[p + "self_attn.v_proj.weight"], P)
         acc(p + "self_attn.v_proj.weight", dw)
+        if p + "self_attn.q_proj.bias" in W:
+            acc(p + "self_attn.q_proj.bias", bias_bwd(dq2, P))
+            acc(p + "self_attn.k_proj.bias", bias_bwd(dk2, P))
+            acc(p + "self_attn.v_proj.bias", bias_bwd(dv2, P))
         dx1 = P.r(P.r(dx1q + dx1k) + dx1v)
         dh0n, dw = rmsnorm_bwd(dx1, h0, W[p + "input_layernorm.weight"], r1, P)
         acc(p + "input_layernorm.weight", dw)

@@ -74,6 +74,10 @@ def llama_param_shapes(cfg):
         s[p + "self_attn.q_proj.weight"] = (nh * d, h)
         s[p + "self_attn.k_proj.weight"] = (nkv * d, h)
         s[p + "self_attn.v_proj.weight"] = (nkv * d, h)
+        if cfg.get("model_type") == "qwen2":       # components/models/qwen2/model.py:80-82: q/k/v projections with bias
+            s[p + "self_attn.q_proj.bias"] = (nh * d,)
+            s[p + "self_attn.k_proj.bias"] = (nkv * d,)
+            s[p + "self_attn.v_proj.bias"] = (nkv * d,)
         s[p + "self_attn.o_proj.weight"] = (h, nh * d)
         s[p + "mlp.gate_proj.weight"] = (f, h)
         s[p + "mlp.up_proj.weight"] = (f, h)
@@ -81,5 +85,6 @@ def llama_param_shapes(cfg):
         s[p + "input_layernorm.weight"] = (h,)
         s[p + "post_attention_layernorm.weight"] = (h,)
     s["model.norm.weight"] = (h,)
-    s["lm_head.weight"] = (v, h)
+    if not cfg.get("tie_word_embeddings", False):
+        s["lm_head.weight"] = (v, h)
     return s

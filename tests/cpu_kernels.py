@@ -75,6 +75,17 @@ def rope_(qk, cos, sin, pos, heads, head_dim, backward=False):
     return qk
 
 
+def bias_rope_(qkv, bias, cos, sin, pos, rope_heads, heads, head_dim):
+    qkv.copy_(_r(qkv.float() + bias.float()[None, :]))
+    return rope_(qkv, cos, sin, pos, rope_heads, head_dim)
+
+
+def colsum_(x, out, accumulate=False):
+    t = x.float().sum(0)
+    out.copy_(_r(_r(t).float() + out.float()) if accumulate else _r(t))
+    return out
+
+
 def swiglu_fwd(gu, out=None):
     F = gu.shape[1] // 2
     g, u = gu[:, :F].float(), gu[:, F:].float()

@@ -35,7 +35,7 @@ dist_env: {{backend: gloo, timeout_minutes: 5}}
 model:
   _target_: nemo_automodel.NeMoAutoModelForCausalLM.from_config
   config:
-    _target_: transformers.LlamaConfig
+    _target_: transformers.{cfg_class}
     vocab_size: {vocab}
     hidden_size: {hidden}
     intermediate_size: {ffn}
@@ -45,8 +45,8 @@ model:
     max_position_embeddings: {seq}
     rms_norm_eps: 1.0e-5
     rope_theta: {theta}
-    tie_word_embeddings: false
-    architectures: [LlamaForCausalLM]
+    tie_word_embeddings: {tied}
+    architectures: [{arch}]
   torch_dtype: {dtype}
   attn_implementation: sdpa
   use_liger_kernel: false
@@ -63,17 +63,24 @@ dataloader: {{_target_: torch.utils.data.DataLoader, batch_size: null}}
 optimizer: {{_target_: torch.optim.AdamW, lr: {lr}, betas: [0.9, 0.95], eps: 1.0e-8, weight_decay: 0.1{opt_extra}}}
 """
 
+_LLAMA = dict(cfg_class="LlamaConfig", arch="LlamaForCausalLM", tied="false")
 CONFIGS = {
     # BASELINE.json configs[0]: d_model 256, L 2, seq 512, world 1 (fp32: the exact-math pin for the oracle)
     "tiny_fp32": dict(gbs=2, lbs=2, steps=3, vocab=1024, hidden=256, ffn=512, layers=2, heads=4, kv=2, seq=512,
-                      theta=10000.0, dtype="float32", lr="1.0e-3", opt_extra=""),
+                      theta=10000.0, dtype="float32", lr="1.0e-3", opt_extra="", **_LLAMA),
     # same shapes in bf16 (params, compute and AdamW states bf16 as torch.optim.AdamW does on bf16 params)
     # 100 steps: the north_star's "step-loss within 1e-3 over 100 steps" curve
     "tiny_bf16": dict(gbs=2, lbs=2, steps=100, vocab=1024, hidden=256, ffn=512, layers=2, heads=4, kv=2, seq=512,
-                      theta=10000.0, dtype="bfloat16", lr="1.0e-3", opt_extra=""),
+                      theta=10000.0, dtype="bfloat16", lr="1.0e-3", opt_extra="", **_LLAMA),
     # head_dim 128 / GQA 4:1 like Llama-3-8B, 2 micro-batches per step (grad accumulation), fp32
     "hd128_fp32": dict(gbs=2, lbs=1, steps=2, vocab=512, hidden=256, ffn=512, layers=2, heads=2, kv=1, seq=256,
-                       theta=500000.0, dtype="float32", lr="1.0e-3", opt_extra=""),
+                       theta=500000.0, dtype="float32", lr="1.0e-3", opt_extra="", **_LLAMA),
+    # Qwen2 (components/models/qwen2/model.py: q/k/v bias, tied embeddings) through the same kernels: head_dim 64, GQA 2:1, bf16, 2 micro-batches
+    "qwen2_tiny_bf16": dict(gbs=2, lbs=1, steps=20, vocab=1024, hidden=256, ffn=512, layers=2, heads=4, kv=2, seq=256,
+                            theta=1000000.0, dtype="bfloat16", lr="1.0e-3", opt_extra="", cfg_class="Qwen2Config", arch="Qwen2ForCausalLM", tied="true"),
+    # the same model untied, fp32: the exact-math pin of the bias path for the oracle
+    "qwen2_tiny_fp32": dict(gbs=2, lbs=2, steps=3, vocab=512, hidden=128, ffn=256, layers=2, heads=2, kv=1, seq=128,
+                            theta=1000000.0, dtype="float32", lr="1.0e-3", opt_extra="", cfg_class="Qwen2Config", arch="Qwen2ForCausalLM", tied="false"),
 }
 
 
@@ -105,7 +112,27 @@ def run(name):
     r.setup()
     model = r.model_parts[0]
     # ---- both sides start from the same portable snapshot (oracle/portable_init.py)
-    sd = model.state_dict()
+    retied = None
+    if c.get("tied") == "true" and model.lm_head.weight.data_ptr() != model.model.embed_tokens.weight.data_ptr():
+        # The reference ties lm_head to the embedding when the config says so (components/models/qwen2/model.py:397-400, and again after
+        # weight loading, components/checkpoint/checkpointing.py:720-722).  Under this image's transformers (5.5.0; the reference pins
+        # 5.8.1) the recipe's from_config path leaves them untied, so the declared state is established here: first through the model's own
+        # tie_weights(), else by sharing the parameter - exactly what tie_weights() does under the pinned version.
+        model.tie_weights()
+        retied = "tie_weights()"
+        if model.lm_head.weight.data_ptr() != model.model.embed_tokens.weight.data_ptr():
+            model.lm_head.weight = model.model.embed_tokens.weight
+            retied = "parameter shared by assignment"
+        # the optimizer was built from the untied parameter list: rebuild its groups from the tied model
+        opt0 = r.optimizer[0]
+        keep = {id(p) for p in model.parameters()}
+        for g_ in opt0.param_groups:
+            g_["params"] = [p for p in g_["params"] if id(p) in keep]
+    sd, seen = {}, set()
+    for k, v in model.state_dict().items():     # tied embeddings list the shared matrix under both names: initialise it once (first name)
+        if v.data_ptr() not in seen:
+            seen.add(v.data_ptr())
+            sd[k] = v
     init = portable_state_dict({k: tuple(v.shape) for k, v in sd.items()}, seed=SEED)
     with torch.no_grad():
         for k, v in sd.items():
@@ -159,7 +186,7 @@ def run(name):
         "num_label_tokens": rec["num_label_tokens"], "lr": rec["lr"], "max_grad_norm": rec.get("max_grad_norm"),
         "num_micro": rec.get("num_micro"), "snap_steps": sorted(snap_steps),
         "torch": torch.__version__, "transformers": transformers.__version__,
-        "model_class": type(model).__name__, "norm_class": type(model.model.norm).__name__,
+        "model_class": type(model).__name__, "retied": retied, "tied": bool(model.lm_head.weight.data_ptr() == model.model.embed_tokens.weight.data_ptr()), "norm_class": type(model.model.norm).__name__,
         "optimizer_class": type(opt).__name__,
         "optimizer": {k: (list(v) if isinstance(v, tuple) else v) for k, v in opt.param_groups[0].items() if k != "params"},
     }, default=str).encode(), dtype=np.uint8)

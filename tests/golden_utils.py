@@ -16,11 +16,14 @@ def load(name):
 
 def model_cfg(meta):
     c = meta["config"]
-    return {
+    out = {
         "vocab_size": c["vocab"], "hidden_size": c["hidden"], "intermediate_size": c["ffn"],
         "num_hidden_layers": c["layers"], "num_attention_heads": c["heads"], "num_key_value_heads": c["kv"],
         "max_position_embeddings": c["seq"], "rms_norm_eps": 1e-5, "rope_theta": c["theta"],
     }
+    if c.get("cfg_class") == "Qwen2Config":
+        out.update(model_type="qwen2", tie_word_embeddings=c.get("tied") == "true")
+    return out
 
 
 def init_params(meta):

@@ -38,7 +38,8 @@ def test_cu_seqlens_from_position_ids():
     assert cu.tolist() == [0, 3, 5, 6, 12] and mx == 6
 
 
-@pytest.mark.parametrize("name,prec,tol", [("tiny_bf16", "bf16", 1e-3), ("hd128_fp32", "bf16", 4e-3)])
+@pytest.mark.parametrize("name,prec,tol", [("tiny_bf16", "bf16", 1e-3), ("hd128_fp32", "bf16", 4e-3), ("qwen2_tiny_bf16", "bf16", 1e-3),
+                                           ("qwen2_tiny_fp32", "bf16", 4e-3)])
 def test_engine_tracks_reference_fixture(name, prec, tol):
     """bf16 engine (CPU stand-in kernels) vs the reference run: loss / grad_norm per step, step-0 grads, weights."""
     z, meta = load(name)
@@ -55,7 +56,9 @@ def test_engine_tracks_reference_fixture(name, prec, tol):
             for i, m in enumerate(mbs):
                 eng.forward_backward(m["input_ids"], m["labels"], None, n, first_micro=i == 0, last_micro=i == len(mbs) - 1)
             for k, g in eng.named_grads().items():
-                check_rel_l2(z, "grad0", k, g.float().numpy(), tol=2e-2)
+                # k_proj.bias: softmax is invariant to a constant added to every key, so this gradient is what RoPE's position dependence leaves
+                # of an exact zero - a sum of cancelling bf16 terms (relative noise ~10x that of the other parameters)
+                check_rel_l2(z, "grad0", k, g.float().numpy(), tol=0.15 if k.endswith("k_proj.bias") else 2e-2)
             loss = float(eng.loss_dev[0]); gn = float(eng.optimizer_step(meta["max_grad_norm"]).sqrt())
         else:
             l, g = eng.train_step(mbs, meta["max_grad_norm"])
@@ -289,10 +292,18 @@ def test_unsupported_configs_are_rejected_loudly():
     base = dict(vocab_size=512, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=1,
                 max_position_embeddings=256, rms_norm_eps=1e-5)
     from automodel_b200.engine import _rope_inv_freq
-    for bad in (dict(model_type="qwen2"), dict(sliding_window=4096), dict(tie_word_embeddings=True), dict(attention_bias=True), dict(mlp_bias=True),
-                dict(hidden_act="gelu"), dict(attention_dropout=0.1)):
+    for bad in (dict(model_type="gemma2"), dict(sliding_window=4096), dict(attention_bias=True), dict(mlp_bias=True), dict(hidden_act="gelu"),
+                dict(attention_dropout=0.1), dict(model_type="qwen2", use_sliding_window=True, sliding_window=128),
+                dict(model_type="qwen2", layer_types=["full_attention", "sliding_attention"])):
         with pytest.raises(ValueError):
             LlamaDims.from_hf(dict(base, **bad))
+    # the Llama-family variants the kernels do cover: Qwen2's q/k/v bias, tied embeddings (Qwen2 <= 1.5B, Llama-3.2-1B)
+    q = LlamaDims.from_hf(dict(base, model_type="qwen2", sliding_window=4096, use_sliding_window=False, tie_word_embeddings=True))
+    assert q.qkv_bias and q.tied
+    names = [sl.name for u in build_layout(q, 2) for sl in u.slots]
+    assert "lm_head.weight" not in names and "model.layers.1.self_attn.v_proj.bias" in names
+    t = LlamaDims.from_hf(dict(base, tie_word_embeddings=True))
+    assert t.tied and not t.qkv_bias
     with pytest.raises(ValueError):
         _rope_inv_freq(LlamaDims.from_hf(dict(base, rope_scaling={"rope_type": "yarn", "factor": 4.0})))
     LlamaDims.from_hf(dict(base, model_type="mistral", sliding_window=None))

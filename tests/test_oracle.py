@@ -6,7 +6,7 @@ from oracle import llama_step as O
 from tests.golden_utils import load, model_cfg, init_params, batches, check_summary
 
 
-@pytest.mark.parametrize("name", ["tiny_fp32", "hd128_fp32"])
+@pytest.mark.parametrize("name", ["tiny_fp32", "hd128_fp32", "qwen2_tiny_fp32"])
 def test_oracle_fp32_matches_reference(name):
     z, meta = load(name)
     cfg = model_cfg(meta)

@@ -152,7 +152,9 @@ def run(args):
             inv_ok = bool(rot.inv_freq.device.type == "cuda" and torch.equal(rot.inv_freq.float(), want))
             have = rot.inv_freq.float().to(dev)
             globals()["_INV_DEV"] = float(((have - want).abs() / want.abs()).max()) if have.shape == want.shape else float("nan")
-            if not inv_ok:
+            globals()["_INV_HAVE"] = {"dtype": str(rot.inv_freq.dtype), "device": str(rot.inv_freq.device), "stock": [float(x) for x in have.cpu()],
+                                      "formula": [float(x) for x in want.cpu()], "stock_equals_bf16_rounded_formula": bool(torch.equal(have, want.to(torch.bfloat16).float()))}
+            if not inv_ok and not args.keep_stock_inv_freq:
                 rot.inv_freq = want
                 rot._cos_cache = rot._sin_cache = None
                 rot.max_seq_len_cached = 0
@@ -170,7 +172,8 @@ def run(args):
     if args.fwd_only:
         return fwd_only(args, r, model, c, dev)
 
-    rec = {"ref_inv_freq_was_initialised": globals().get("_INV_OK"), "ref_inv_freq_max_rel_dev_from_formula": globals().get("_INV_DEV"), "loss": [], "grad_norm": [], "step_ms": [], "tps": [], "ids_crc": [], "num_label_tokens": [], "mem_gb": []}
+    rec = {"ref_inv_freq_was_initialised": globals().get("_INV_OK"), "ref_inv_freq_max_rel_dev_from_formula": globals().get("_INV_DEV"),
+           "ref_inv_freq": globals().get("_INV_HAVE"), "kept_stock_inv_freq": bool(args.keep_stock_inv_freq), "loss": [], "grad_norm": [], "step_ms": [], "tps": [], "ids_crc": [], "num_label_tokens": [], "mem_gb": []}
     orig = r._run_train_optim_step
 
     def spy(batches, max_grad_norm=None):
@@ -367,6 +370,7 @@ if __name__ == "__main__":
     ap.add_argument("--attn", default="sdpa")
     ap.add_argument("--loss", default="reference", choices=["reference", "fused"])
     ap.add_argument("--reduce-dtype", default=None)
+    ap.add_argument("--keep-stock-inv-freq", action="store_true", help="do not repair the reference's RoPE inv_freq buffer (see the guard in run())")
     ap.add_argument("--sdpa-backend", default=None, choices=["flash", "cudnn", "efficient", "math"])
     ap.add_argument("--dtype", default="bfloat16", help="torch_dtype of the reference model (float32: exact-arithmetic run of the same weights)")
     ap.add_argument("--fwd-only", type=int, default=0, help="noise-floor mode: loss of the initial weights on N batches, no training")
