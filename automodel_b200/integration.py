@@ -59,7 +59,14 @@ def register(ops=None, device=None, patch_sync_ctx=True):
                         rpg = dm["dp_replicate"].get_group()
                 else:
                     pg = dm.get_group()
-            return B200ShardedManager(config, process_group=pg, replica_group=rpg, device=device, ops=ops)
+            def reference_manager():
+                """The reference's own FSDP2 manager over the same mesh, configured from the keys the two configs share."""
+                import dataclasses
+                from nemo_automodel.components.distributed.config import FSDP2Config
+                shared = {f.name: getattr(config, f.name) for f in dataclasses.fields(FSDP2Config) if hasattr(config, f.name)}
+                return orig_inst(FSDP2Config(**shared), mesh)
+
+            return B200ShardedManager(config, process_group=pg, replica_group=rpg, device=device, ops=ops, fallback=reference_manager)
         return orig_inst(config, mesh)
 
     _infra._instantiate_distributed = _instantiate_distributed

@@ -298,7 +298,13 @@ class B200MaskedCrossEntropy(nn.Module):
     def forward(self, logits, labels, mask=None, num_label_tokens: Optional[int] = None):
         model = getattr(logits, "_b200_model", None)
         if model is None:
-            raise TypeError("B200MaskedCrossEntropy needs the logits of a B200CausalLM forward (no torch fallback on this path)")
+            # logits of a model that runs on the reference's own path (B200ShardedManager.fallback): the reference's MaskedCrossEntropy
+            # computation itself (components/loss/masked_ce.py:73-89) - fp32 upcast, sum over label tokens / num_label_tokens
+            import torch.nn.functional as F
+            if mask is not None:
+                labels = labels.masked_fill(mask == 0, IGNORE_INDEX)
+            loss = F.cross_entropy(logits.float().view(-1, logits.shape[-1]), labels.view(-1), ignore_index=IGNORE_INDEX, reduction="sum")
+            return loss / num_label_tokens if num_label_tokens is not None else loss
         if mask is not None:
             raise NotImplementedError("mask= is not supported; pre-mask the labels with -100 (what the reference does internally)")
         if num_label_tokens is None:
@@ -308,7 +314,20 @@ class B200MaskedCrossEntropy(nn.Module):
 
 
 class B200FusedAdamW(torch.optim.Optimizer):
-    """optimizer `_target_`: fused AdamW on the flat shards of the engine that owns `params`."""
+    """optimizer `_target_`: fused AdamW on the flat shards of the engine that owns `params`.  Parameters that belong to NO engine (the
+    strategy routed the model to the reference's FSDP2 path, see B200ShardedManager.fallback) get a plain torch.optim.AdamW with the same
+    hyper-parameters - the reference's default optimizer - so the YAML keeps working unchanged."""
+
+    def __new__(cls, params=None, *args, **kwargs):
+        if params is not None:
+            params = list(params)
+            flat = [p for g in params for p in g["params"]] if params and isinstance(params[0], dict) else params
+            if flat and all(getattr(p, "_b200_engine", None) is None for p in flat):
+                kw = {k: v for k, v in kwargs.items() if k in ("lr", "betas", "eps", "weight_decay", "amsgrad", "maximize", "foreach", "fused", "capturable", "differentiable")}
+                return torch.optim.AdamW(params, *args, **kw)        # not an instance of cls: __init__ below is skipped
+        obj = super().__new__(cls)
+        obj._materialised_params = params      # `params` may be a generator: __init__ receives the same (now exhausted) object
+        return obj
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=False, maximize=False, foreach=None,
                  fused=None, capturable=False, differentiable=False):
@@ -316,7 +335,7 @@ class B200FusedAdamW(torch.optim.Optimizer):
         # fused, capturable) mean nothing here, options that change the mathematics are refused
         if amsgrad or maximize or differentiable:
             raise NotImplementedError("B200FusedAdamW implements plain AdamW (amsgrad / maximize / differentiable are not supported)")
-        params = list(params)
+        params = self.__dict__.pop("_materialised_params", None) or list(params)
         engines = {id(getattr(p, "_b200_engine", None)): getattr(p, "_b200_engine", None) for p in params}
         if len(engines) != 1 or None in engines.values():
             raise TypeError("B200FusedAdamW needs the parameters of ONE B200CausalLM")
@@ -398,10 +417,26 @@ class B200FusedAdamW(torch.optim.Optimizer):
 class B200ShardedManager:
     """`.parallelize(model)` of the new distributed strategy."""
 
-    def __init__(self, config: B200ShardedConfig, process_group=None, device=None, ops=None, replica_group=None):
+    def __init__(self, config: B200ShardedConfig, process_group=None, device=None, ops=None, replica_group=None, fallback=None):
         self.config, self.pg, self.device, self.ops, self.rpg = config, process_group, device, ops, replica_group
+        # fallback: callable returning the reference's own manager (FSDP2Manager over the same mesh).  north_star: "any HF config the
+        # reference accepts runs unchanged" - a model this engine does not implement (another architecture, PEFT adapters, frozen
+        # parameters, an unsupported RoPE variant ...) is handed to the unmodified reference path instead of failing the job.
+        self.fallback = fallback
+        self.used_fallback = None     # reason string once parallelize() has routed a model to the reference path
 
     def parallelize(self, model, optimizer_defaults=None):
+        if self.fallback is None:
+            return self._parallelize(model, optimizer_defaults)
+        try:
+            return self._parallelize(model, optimizer_defaults)
+        except (ValueError, NotImplementedError) as e:
+            import logging
+            self.used_fallback = f"{type(e).__name__}: {e}"
+            logging.getLogger(__name__).warning("strategy b200_sharded: %s -> training this model on the reference's FSDP2 path", self.used_fallback)
+            return self.fallback().parallelize(model)
+
+    def _parallelize(self, model, optimizer_defaults=None):
         cfg = model.config if hasattr(model, "config") else model
         dev = self.device if self.device is not None else torch.device("cuda", torch.cuda.current_device())
         od = optimizer_defaults or {}

@@ -50,6 +50,9 @@ def main(name, loss_kind, steps):
     if loss_kind == "fused_loss":
         y = y.replace("_target_: nemo_automodel.components.loss.masked_ce.MaskedCrossEntropy", "_target_: automodel_b200.recipe.B200MaskedCrossEntropy")
     assert "b200_sharded" in y and "B200FusedAdamW" in y
+    if os.environ.get("B200_DROPIN_FALLBACK"):       # e.g. "attention_bias: true": a Llama variant the engine refuses
+        y = y.replace("    tie_word_embeddings: false\n", "    tie_word_embeddings: false\n    " + os.environ["B200_DROPIN_FALLBACK"] + "\n")
+        assert os.environ["B200_DROPIN_FALLBACK"] in y
     ck = os.environ.get("B200_DROPIN_CKPT")     # "<dir>" or "<dir>:<restore_from>": the reference's own Checkpointer, every 2 steps
     if ck:
         ck_dir, _, restore = ck.partition(":")
@@ -79,6 +82,21 @@ def main(name, loss_kind, steps):
         r = TrainFinetuneRecipeForNextTokenPrediction(cfg)
     r.setup()
     model = r.model_parts[0]
+    if os.environ.get("B200_DROPIN_FALLBACK"):
+        # a config the engine does not implement: the strategy must have routed the model to the reference's own path
+        losses = []
+        orig_fb = r._run_train_optim_step
+
+        def spy_fb(batches, max_grad_norm=None):
+            m = orig_fb(batches, max_grad_norm)
+            losses.append(float(m.metrics["loss"]))
+            return m
+
+        r._run_train_optim_step = spy_fb
+        r.run_train_validation_loop()
+        sys.stdout.write("\nB200_DROPIN_RESULT " + json.dumps({"loss": losses, "model_class": type(model).__name__, "optimizer_class": type(r.optimizer[0]).__name__,
+                                                               "loss_class": type(r.loss_fn).__name__, "has_engine": hasattr(model, "engine")}) + "\n")
+        return
     z, meta = load(name)
     # what the recipe's own initialisation left in the flat buffers (from_config: Checkpointer.initialize_model_weights, before or after
     # sharding depending on the world size)

@@ -141,6 +141,35 @@ def test_parallelize_rejects_models_it_would_not_train_faithfully():
         mgr.parallelize(frozen)
 
 
+def test_fallback_routes_unsupported_models_to_the_reference_manager():
+    """With a fallback (what integration.register() installs: the reference's FSDP2Manager over the same mesh) the same rejections
+    become a hand-over instead of an error, and the B200 optimizer / loss targets keep working on the foreign model."""
+    import transformers
+    from automodel_b200.recipe import B200FusedAdamW, B200MaskedCrossEntropy
+    z, meta = load("hd128_fp32")
+    c = meta["config"]
+    hf_cfg = transformers.LlamaConfig(vocab_size=c["vocab"], hidden_size=c["hidden"], intermediate_size=c["ffn"], num_hidden_layers=c["layers"],
+                                      num_attention_heads=c["heads"], num_key_value_heads=c["kv"], max_position_embeddings=c["seq"],
+                                      rope_theta=c["theta"], tie_word_embeddings=False, attention_bias=True)
+
+    class _RefManager:
+        def parallelize(self, model):
+            model.handled_by_reference = True
+            return model
+
+    mgr = B200ShardedManager(B200ShardedConfig(max_tokens=c["seq"]), device=torch.device("cpu"), ops=cpu_kernels, fallback=_RefManager)
+    ref_model = transformers.LlamaForCausalLM(hf_cfg)
+    out = mgr.parallelize(ref_model)
+    assert out is ref_model and out.handled_by_reference and "attention_bias" in mgr.used_fallback
+    opt = B200FusedAdamW(params=out.parameters(), lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1)
+    assert type(opt) is torch.optim.AdamW and opt.param_groups[0]["betas"] == (0.9, 0.95)
+    logits = torch.randn(2, 8, 32)
+    lab = torch.randint(0, 32, (2, 8)); lab[0, :3] = -100
+    n = int((lab != -100).sum())
+    got = B200MaskedCrossEntropy()(logits=logits, labels=lab, num_label_tokens=n)
+    torch.testing.assert_close(got, _TorchMaskedCE()(logits=logits, labels=lab, num_label_tokens=n))
+
+
 def test_foreign_optimizer_is_detected():
     """torch.optim.AdamW on the facade's parameter views would skip the clip and, sharded, read reduce-scattered buffers: the next
     training forward after a clip that was not followed by B200FusedAdamW.step() fails loudly."""

@@ -201,3 +201,14 @@ def test_from_pretrained_through_the_reference_loader(tmp_path):
     rec = _run("hd128_fp32", "reference_loss", 1, B200_DROPIN_PRETRAINED=str(tmp_path / "hf"))
     assert rec["model_class"] == "B200CausalLM" and rec["pretrained_tensors"] == 2 + 9 * c["layers"] + 1
     assert rec["pretrained_mismatch"] == []
+
+
+@pytest.mark.parametrize("loss_kind", ["reference_loss", "fused_loss"])
+def test_unsupported_config_runs_on_the_reference_path(loss_kind):
+    """north_star: "any HF config the reference accepts runs unchanged".  A Llama variant the engine refuses (bias on every attention
+    projection) under `strategy: b200_sharded` + the B200 optimizer / loss `_target_`s trains on the reference's OWN model and FSDP2 path:
+    the strategy hands the model back, B200FusedAdamW degrades to torch.optim.AdamW, B200MaskedCrossEntropy to the reference formula."""
+    res = _run("tiny_bf16", loss_kind, 4, B200_DROPIN_FALLBACK="attention_bias: true")
+    assert res["model_class"] == "LlamaForCausalLM" and not res["has_engine"]
+    assert res["optimizer_class"] == "AdamW"
+    assert len(res["loss"]) == 4 and all(6.5 < l < 7.5 for l in res["loss"])

@@ -27,4 +27,4 @@ except Exception as e:
 PY
 done
 # HSDP 2 x 4 over NCCL + symmetric-memory collectives inside each shard group of 4
-timeout 120 $TR --master-port 29731 tools/hsdp_check.py > $O/r2_hsdp_2x4.log 2>&1; echo "hsdp 2x4 rc=$?"; tail -3 $O/r2_hsdp_2x4.log
+timeout 100 $TR --master-port 29731 tools/hsdp_check.py > $O/r2_hsdp_2x4.log 2>&1; echo "hsdp 2x4 rc=$?"; tail -3 $O/r2_hsdp_2x4.log
