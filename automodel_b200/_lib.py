@@ -45,6 +45,7 @@ SIGNATURES = {
     "b200_ctx_has_multicast": (_i, [_vp, _i]),
     "b200_reducescatter_layer": (_i, [_vp, _i, _sz, _i64, _i, _i, _vp]),
     "b200_allgather_layer": (_i, [_vp, _i, _sz, _i64, _i, _i, _vp]),
+    "b200_allreduce_scalars": (_i, [_vp, _vp, _i, _vp]),
 }
 
 

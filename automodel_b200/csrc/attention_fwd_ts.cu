@@ -32,30 +32,6 @@ __device__ __forceinline__ float ex2a(float x) {
   return y;
 }
 
-// 2^x for x <= 0 on the FMA / integer pipes (two elements per call, packed): round-to-nearest split x = n + f with the 1.5*2^23 magic
-// constant, degree-3 minimax polynomial of 2^f on [-0.5, 0.5] (max relative error 7.5e-5, 1/27 of a bf16 half-ulp), n added into the
-// exponent field.  Takes MUFU.EX2 (16 results per clock per SM - exactly as many clocks per kv tile as the tile's MMAs) off the
-// critical resource for a fraction of the elements.
-__device__ __forceinline__ void ex2_poly2(uint64_t x2, float& p0, float& p1) {
-  float x0, x1;
-  f2_unpack(x2, x0, x1);
-  x0 = fmaxf(x0, -125.f);   // masked (-inf) and underflowing scores: a denormal-sized weight, i.e. zero at bf16 precision
-  x1 = fmaxf(x1, -125.f);
-  const uint64_t x = f2_pack(x0, x1);
-  const uint64_t magic = f2_pack(12582912.f, 12582912.f);
-  const uint64_t xr = f2_add(x, magic);                                  // low mantissa bits = round(x) (two's complement)
-  const uint64_t nf = f2_add(xr, f2_pack(-12582912.f, -12582912.f));     // round(x) as a float
-  const uint64_t f = f2_add(x, f2_mul(nf, f2_pack(-1.f, -1.f)));         // f in [-0.5, 0.5]
-  uint64_t p = f2_fma(f2_pack(0.0551716574f, 0.0551716574f), f, f2_pack(0.2426111251f, 0.2426111251f));
-  p = f2_fma(p, f, f2_pack(0.6932609677f, 0.6932609677f));
-  p = f2_fma(p, f, f2_pack(0.9999280572f, 0.9999280572f));
-  float a, b, r0, r1;
-  f2_unpack(p, a, b);
-  f2_unpack(xr, r0, r1);
-  p0 = __uint_as_float(__float_as_uint(a) + (__float_as_uint(r0) << 23));
-  p1 = __uint_as_float(__float_as_uint(b) + (__float_as_uint(r1) << 23));
-}
-
 template <int D>
 struct Smem {
   static constexpr int TILE_Q = 128 * D * 2;   // D/64 boxes of [128 rows x 64 cols]
@@ -63,14 +39,18 @@ struct Smem {
   static constexpr int Q_OFF = 0;
   static constexpr int K_OFF = TILE_Q;
   static constexpr int V_OFF = TILE_Q + 2 * TILE_KV;
-  static constexpr int BAR_OFF = TILE_Q + 4 * TILE_KV;
+  static constexpr int XCH_OFF = TILE_Q + 4 * TILE_KV;      // float [3][2][128]: row-max exchange (two tile parities) and final row-sum exchange
+  static constexpr int BAR_OFF = XCH_OFF + 3 * 2 * 128 * 4;
   static constexpr int NUM_BARS = 13;
-  static constexpr int DYN = BAR_OFF + NUM_BARS * 8 + 16;  // 98,424 B at D=128: two CTAs per SM
+  static constexpr int DYN = BAR_OFF + NUM_BARS * 8 + 16;  // 101,496 B at D=128: two CTAs per SM
 };
 
-// EMU: of every 8 consecutive kv columns, the first EMU (0, 2 or 4) take the polynomial path, the rest MUFU.EX2
-template <int D, int EMU>
-__global__ void __launch_bounds__(192, 2)
+// HALVES: softmax warps per TMEM lane quarter.  1: one thread owns a whole 64-column row of the tile (4 softmax warps).  2: two warps
+// share the rows of a quarter, 32 columns each (8 softmax warps, 4 per scheduler with both CTAs of the SM): the row maximum is exchanged
+// through shared memory once per tile, the row sums only at the end; twice the warps to hide the MUFU / TMEM latencies that leave the
+// 4-warp version at 53 % of both the tensor and the MUFU pipe.
+template <int D, int HALVES>
+__global__ void __launch_bounds__(64 + 128 * HALVES, 2)
 attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    __nv_bfloat16* __restrict__ o, float* __restrict__ lse, const int* __restrict__ cu_seqlens, int64_t ldo, int Hq, int Hkv, int T,
                    float scale_log2) {
@@ -113,7 +93,7 @@ attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
     }
-    mbar_init(p_ready, 4);
+    mbar_init(p_ready, 4 * HALVES);
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
@@ -181,48 +161,57 @@ attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else {
-    const int quad = warp & 3;
+    constexpr int CW = 64 / HALVES;          // kv columns of a tile per thread
+    constexpr int OC = D / 32 / HALVES;      // 32-column chunks of O per thread (rescale / epilogue)
+    const int quad = warp & 3;               // TMEM lane quarter this warp may access (warp id % 4)
+    const int half = (warp - 2) >> 2;        // which CW columns of the tile / which O chunks
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const int qrow = m0 + r;
-    float m_used = 0.f, l_sum = 0.f;   // m_used: running row maximum in the exp2 domain (score * scale * log2 e)
+    float* xch = reinterpret_cast<float*>(smem + L::XCH_OFF);
+    float m_used = 0.f, l_sum = 0.f;   // m_used: running row maximum in the exp2 domain (score * scale * log2 e); l_sum: this thread's columns only
     const uint64_t scale2 = f2_pack(scale_log2, scale_log2);
     for (int j = 0; j < n_kv; ++j) {
       const int st = j & 1;
       mbar_wait(&s_full[st], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t v[2][32];
-      tmem_ld_32x32b_x32(tS0 + lane_addr + st * 64, v[0]);
-      tmem_ld_32x32b_x32(tS0 + lane_addr + st * 64 + 32, v[1]);
+      uint32_t v[CW];
+#pragma unroll
+      for (int c = 0; c < CW / 32; ++c) tmem_ld_32x32b_x32(tS0 + lane_addr + st * 64 + half * CW + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
       tmem_ld_wait();
 
       if ((j * 64 + 63 > m0) || ((j + 1) * 64 > len)) {   // tiles that touch the diagonal or the end of the document
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int kv = j * 64 + c * 32 + e;
-            if (kv > qrow || kv >= len) v[c][e] = 0xff800000u;   // -inf
-          }
+        for (int e = 0; e < CW; ++e) {
+          const int kv = j * 64 + half * CW + e;
+          if (kv > qrow || kv >= len) v[e] = 0xff800000u;   // -inf
+        }
       }
-      // row max of the raw scores (scale > 0: the max commutes with the scaling); four independent FMNMX3 chains of 8 instead of one of 32
+      // row max of the raw scores (scale > 0: the max commutes with the scaling); four independent FMNMX3 chains
       float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) mxa[(e >> 1) & 3] = fmax3(mxa[(e >> 1) & 3], __uint_as_float(v[c][e]), __uint_as_float(v[c][e + 1]));
-      float mx = fmaxf(fmax3(mxa[0], mxa[1], mxa[2]), mxa[3]) * scale_log2;
+      for (int e = 0; e < CW; e += 2) mxa[(e >> 1) & 3] = fmax3(mxa[(e >> 1) & 3], __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+      float mx = fmaxf(fmax3(mxa[0], mxa[1], mxa[2]), mxa[3]);
+      if (HALVES == 2) {
+        // the other warp of this lane quarter holds the other 32 columns of the same rows: exchange through smem (buffer = tile parity,
+        // so one named barrier per tile is enough)
+        float* buf = xch + st * 256;
+        buf[half * 128 + r] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        mx = fmaxf(mx, buf[(half ^ 1) * 128 + r]);
+      }
+      mx *= scale_log2;
       if (j == 0) {
         m_used = (mx == -INFINITY) ? 0.f : mx;
       } else {
-        const bool grow = mx > m_used + 8.f;  // lazy rescale (P <= 2^8)
+        const bool grow = mx > m_used + 8.f;  // lazy rescale (P <= 2^8); both warps of a quarter see the same rows, maxima and decision
         if (__any_sync(0xffffffffu, grow)) {
           mbar_wait(pv_done, (j - 1) & 1);
           tc_fence_after();
           const float f = grow ? ex2a(m_used - mx) : 1.f;
           const uint64_t f2 = f2_pack(f, f);
 #pragma unroll
-          for (int c = 0; c < D / 32; ++c) {
+          for (int c = half * OC; c < half * OC + OC; ++c) {
             uint32_t ov[32];
             tmem_ld_32x32b_x32(tO + lane_addr + c * 32, ov);
             tmem_ld_wait();
@@ -241,44 +230,45 @@ attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
       const uint64_t neg_m = f2_pack(-m_used, -m_used);
-      uint32_t pk[32];
+      uint32_t pk[CW / 2];
       uint64_t sum2[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(v[c][e]), __uint_as_float(v[c][e + 1])), scale2, neg_m);
-          float p0, p1;
-          if ((e & 7) < EMU) {
-            ex2_poly2(x2, p0, p1);
-          } else {
-            float x0, x1;
-            f2_unpack(x2, x0, x1);
-            p0 = ex2a(x0);
-            p1 = ex2a(x1);
-          }
-          sum2[(e >> 1) & 1] = f2_add(sum2[(e >> 1) & 1], f2_pack(p0, p1));
-          pk[c * 16 + (e >> 1)] = pack_bf16x2(p0, p1);
-        }
+      for (int e = 0; e < CW; e += 2) {
+        float x0, x1;
+        f2_unpack(f2_fma(f2_pack(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), scale2, neg_m), x0, x1);
+        const float p0 = ex2a(x0), p1 = ex2a(x1);
+        sum2[(e >> 1) & 1] = f2_add(sum2[(e >> 1) & 1], f2_pack(p0, p1));
+        pk[e >> 1] = pack_bf16x2(p0, p1);
       }
       float sa, sb;
       f2_unpack(f2_add(sum2[0], sum2[1]), sa, sb);
       l_sum += sa + sb;
-      // P_j (32 columns of bf16 pairs) over the first half of S_j: this thread has read its whole row of S_j above
-      tmem_st_32x32b_x32(tS0 + lane_addr + st * 64, pk);
+      // P_j (bf16 pairs: CW/2 columns per thread) over the first 32 columns of S_j - every thread that reads those columns of this row
+      // has done so: with HALVES == 2 the half-0 warp loaded them above and the named barrier ordered that load before this store
+      if constexpr (HALVES == 1) {
+        tmem_st_32x32b_x32(tS0 + lane_addr + st * 64, pk);
+      } else {
+        tmem_st_32x32b_x16(tS0 + lane_addr + st * 64 + half * 16, pk);
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
     }
+    if (HALVES == 2) {       // row sums of the two column halves (same m_used and rescale history in both)
+      float* buf = xch + 2 * 256;
+      buf[half * 128 + r] = l_sum;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+      l_sum += buf[(half ^ 1) * 128 + r];
+    }
     mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
     const float inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
     const bool valid = qrow < len;
-    if (valid) lse[static_cast<int64_t>(h) * T + s0 + qrow] = (m_used + log2f(l_sum)) * 0.6931471805599453f;
+    if (valid && half == 0) lse[static_cast<int64_t>(h) * T + s0 + qrow] = (m_used + log2f(l_sum)) * 0.6931471805599453f;
     __nv_bfloat16* orow = o + static_cast<int64_t>(s0 + qrow) * ldo + h * D;
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = half * OC; c < half * OC + OC; ++c) {
       uint32_t ov[32];
       tmem_ld_32x32b_x32(tO + lane_addr + c * 32, ov);
       tmem_ld_wait();
@@ -303,11 +293,11 @@ attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-template <int D, int EMU>
+template <int D, int HALVES>
 static int launch(const void* q, const void* k, const void* v, void* o, float* lse, const int* cu, int nseq, int max_len, int64_t ldq, int64_t ldk,
                   int64_t ldv, int64_t ldo, int Hq, int Hkv, int T, float scale, cudaStream_t st) {
   using L = Smem<D>;
-  auto kern = attn_fwd_ts_kernel<D, EMU>;
+  auto kern = attn_fwd_ts_kernel<D, HALVES>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN);
@@ -320,29 +310,27 @@ static int launch(const void* q, const void* k, const void* v, void* o, float* l
   if ((rc = make_tmap_2d_bf16(&tk, k, T, static_cast<uint64_t>(Hkv) * D, ldk, 64, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tv, v, T, static_cast<uint64_t>(Hkv) * D, ldv, 64, 64))) return rc;
   dim3 grid((max_len + 127) / 128, Hq, nseq);
-  kern<<<grid, 192, L::DYN, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(o), lse, cu, ldo, Hq, Hkv, T, scale * 1.4426950408889634f);
+  kern<<<grid, 64 + 128 * HALVES, L::DYN, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(o), lse, cu, ldo, Hq, Hkv, T, scale * 1.4426950408889634f);
   B200_CHECK_LAUNCH("attn_fwd_ts");
   return 0;
 }
 
 }  // namespace fwdts
 
-// emu: 0, 2 or 4 of every 8 exponentials on the FMA pipe (A/B knob; the default is chosen in c_api.cu)
+// halves: 1 = four softmax warps per CTA (one thread per tile row), 2 = eight (two threads per row)
 int attn_fwd_ts(const void* q, const void* k, const void* v, void* o, float* lse, const int* cu_seqlens, int nseq, int max_len, int64_t ldq,
-                int64_t ldk, int64_t ldv, int64_t ldo, int Hq, int Hkv, int D, int T, float scale, int emu, cudaStream_t st) {
+                int64_t ldk, int64_t ldv, int64_t ldo, int Hq, int Hkv, int D, int T, float scale, int halves, cudaStream_t st) {
   if (Hq % Hkv) return set_error(B200_ERR_ARG, "attn: Hq %% Hkv != 0");
   if ((ldq | ldk | ldv | ldo) % 8) return set_error(B200_ERR_ARG, "attn: row pitches must be multiples of 8 elements");
   if (scale <= 0.f) return set_error(B200_ERR_ARG, "attn: scale must be positive");
-#define B200_FWDTS(DD, EE) return fwdts::launch<DD, EE>(q, k, v, o, lse, cu_seqlens, nseq, max_len, ldq, ldk, ldv, ldo, Hq, Hkv, T, scale, st)
+#define B200_FWDTS(DD, HH) return fwdts::launch<DD, HH>(q, k, v, o, lse, cu_seqlens, nseq, max_len, ldq, ldk, ldv, ldo, Hq, Hkv, T, scale, st)
   if (D == 128) {
-    if (emu == 4) B200_FWDTS(128, 4);
-    if (emu == 2) B200_FWDTS(128, 2);
-    B200_FWDTS(128, 0);
+    if (halves == 2) B200_FWDTS(128, 2);
+    B200_FWDTS(128, 1);
   }
   if (D == 64) {
-    if (emu == 4) B200_FWDTS(64, 4);
-    if (emu == 2) B200_FWDTS(64, 2);
-    B200_FWDTS(64, 0);
+    if (halves == 2) B200_FWDTS(64, 2);
+    B200_FWDTS(64, 1);
   }
 #undef B200_FWDTS
   return set_error(B200_ERR_UNSUPPORTED, "attn: head_dim %d not in {64,128}", D);

@@ -59,12 +59,14 @@ int ctx_register_buffer(CommCtx*, int, void* const*, void*, size_t);
 int ctx_has_multicast(const CommCtx*, int);
 int reducescatter_layer(CommCtx*, int, size_t, int64_t, int, int, cudaStream_t);
 int allgather_layer(CommCtx*, int, size_t, int64_t, int, int, cudaStream_t);
+int allreduce_scalars(CommCtx*, float*, int, cudaStream_t);
+size_t ctx_signal_pad_bytes();
 
 int attn_fwd_tc64(const void*, const void*, const void*, void*, float*, const int*, int, int, int64_t, int64_t, int64_t, int64_t, int, int,
                   int, int, float, cudaStream_t);
 int attn_fwd_ts(const void*, const void*, const void*, void*, float*, const int*, int, int, int64_t, int64_t, int64_t, int64_t, int, int,
                 int, int, float, int, cudaStream_t);
-static int g_attn_fwd_variant = 2;  // 2 (default): P kept in tensor memory, packed-fp32 softmax (attention_fwd_ts.cu, 902 TFLOP/s); 1: attention_fwd64.cu (624); 0: attention_tc.cu forward (510); 3 / 4: variant 2 with 2 / 4 of every 8 exponentials on the FMA pipe (861 / 816: MUFU is not the limiter)
+static int g_attn_fwd_variant = 2;  // 2 (default): P kept in tensor memory, packed-fp32 softmax (attention_fwd_ts.cu, 902 TFLOP/s); 1: attention_fwd64.cu (624); 0: attention_tc.cu forward (510); 3: variant 2 with eight softmax warps per CTA
 
 // debug option: 1 (default) = tcgen05/TMEM attention, 0 = the mma.sync v1 kernels (kept for bisecting only)
 static int g_attn_impl = 1;
@@ -196,9 +198,9 @@ int b200_embed_bwd(const int* ids, const void* dh, void* dW, int* workspace, int
 int b200_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const int* cu_seqlens, int nseq, int max_seqlen,
                   int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int Hq, int Hkv, int head_dim, int total_tokens, float scale,
                   b200_stream_t stream) {
-  if (g_attn_impl == 1 && g_attn_fwd_variant >= 2)   // 2: every exponential on MUFU; 3 / 4: 2 / 4 of every 8 on the FMA pipe (polynomial)
+  if (g_attn_impl == 1 && g_attn_fwd_variant >= 2)   // 2: four softmax warps per CTA; 3: eight (two threads per tile row)
     return attn_fwd_ts(q, k, v, o, lse, cu_seqlens, nseq, max_seqlen, ldq, ldk, ldv, ldo, Hq, Hkv, head_dim, total_tokens, scale,
-                       g_attn_fwd_variant == 2 ? 0 : (g_attn_fwd_variant == 3 ? 2 : 4), S(stream));
+                       g_attn_fwd_variant == 3 ? 2 : 1, S(stream));
   if (g_attn_impl == 1 && g_attn_fwd_variant == 1)
     return attn_fwd_tc64(q, k, v, o, lse, cu_seqlens, nseq, max_seqlen, ldq, ldk, ldv, ldo, Hq, Hkv, head_dim, total_tokens, scale, S(stream));
   if (g_attn_impl == 1)
@@ -240,7 +242,10 @@ int b200_ctx_register_buffer(b200_ctx* ctx, int slot, void* const* peer_ptrs, vo
   return ctx_register_buffer(reinterpret_cast<CommCtx*>(ctx), slot, peer_ptrs, multicast_ptr, bytes);
 }
 int b200_ctx_has_multicast(const b200_ctx* ctx, int slot) { return ctx_has_multicast(reinterpret_cast<const CommCtx*>(ctx), slot); }
-size_t b200_ctx_signal_pad_bytes(void) { return 2 * 64 * 8 * sizeof(uint32_t); }
+size_t b200_ctx_signal_pad_bytes(void) { return ctx_signal_pad_bytes(); }
+int b200_allreduce_scalars(b200_ctx* ctx, float* vals, int n, b200_stream_t stream) {
+  return allreduce_scalars(reinterpret_cast<CommCtx*>(ctx), vals, n, S(stream));
+}
 int b200_reducescatter_layer(b200_ctx* ctx, int slot, size_t byte_offset, int64_t shard_elems, int mode, int ctas, b200_stream_t stream) {
   return reducescatter_layer(reinterpret_cast<CommCtx*>(ctx), slot, byte_offset, shard_elems, mode, ctas, S(stream));
 }

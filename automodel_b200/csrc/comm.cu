@@ -37,10 +37,16 @@ struct SymBuffer {
   size_t bytes;
 };
 
+constexpr int kPadFamilies = 3;            // reduce-scatter, all-gather, scalar all-reduce
+constexpr int kMaxScalars = 16;
+constexpr size_t kFlagBytes = kPadFamilies * kPadWordsPerFamily * sizeof(uint32_t);
+constexpr size_t kPadBytes = kFlagBytes + 2 * kMaxScalars * kMaxWorld * sizeof(float);   // + exchange area [parity][slot][rank]
+
 struct CommCtx {
   int rank, world;
+  unsigned scalar_calls;
   SymBuffer buf[kMaxBuffers];
-  uint32_t* pad[kMaxWorld];   // symmetric signal pad: 2 families (reduce-scatter, all-gather) x kPadWordsPerFamily words, zero-initialised
+  uint32_t* pad[kMaxWorld];   // symmetric signal pad: kPadFamilies x kPadWordsPerFamily flag words + the scalar exchange area, zero-initialised
   size_t pad_bytes;
   long long timeout_ns;
 };
@@ -232,6 +238,35 @@ __global__ void __launch_bounds__(512, 2) all_gather_kernel(Peers c, size_t off,
   cross_rank_barrier(c, 1, blockIdx.x);
 }
 
+// ---------------------------------------------------------------- scalar all-reduce (grad-norm^2, reported loss)
+// vals[0..n) := sum over ranks, in rank order on every rank (bit-identical results everywhere).  One warp: every rank stores its values
+// into slot [parity][j][rank] of EVERY rank's exchange area (remote stores over NVLink), the ranks meet, and each sums its local copy.
+// Keeps NCCL out of the step: with these kernels, the reduce-scatters and the all-gathers on ONE stream, every cross-rank wait of the
+// step is part of a single sequence that is identical on all ranks, so no launch-queue aliasing with a second spinning kernel family
+// (NCCL's) can close a cycle.
+__global__ void __launch_bounds__(32) allreduce_scalars_kernel(Peers c, float* __restrict__ vals, int n, int parity) {
+  const int j = threadIdx.x;
+  const size_t xoff = kFlagBytes + static_cast<size_t>(parity) * kMaxScalars * kMaxWorld * sizeof(float);
+  if (j < n) {
+    const float v = vals[j];
+    for (int p = 0; p < c.world; ++p) {
+      float* dst = reinterpret_cast<float*>(reinterpret_cast<char*>(c.pad[p]) + xoff) + j * kMaxWorld + c.rank;
+      asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst), "f"(v) : "memory");
+    }
+  }
+  cross_rank_barrier(c, 2, 0);
+  if (j < n) {
+    const float* src = reinterpret_cast<const float*>(reinterpret_cast<const char*>(c.pad[c.rank]) + xoff) + j * kMaxWorld;
+    float s = 0.f;
+    for (int r = 0; r < c.world; ++r) {
+      float t;
+      asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(t) : "l"(src + r) : "memory");
+      s += t;
+    }
+    vals[j] = s;
+  }
+}
+
 // ---------------------------------------------------------------- host side
 static Peers make_peers(const CommCtx* c, int slot) {
   Peers p;
@@ -254,6 +289,7 @@ int ctx_create(CommCtx** out, int rank, int world) {
   c->rank = rank;
   c->world = world;
   c->timeout_ns = 60LL * 1000 * 1000 * 1000;
+  c->scalar_calls = 0;
   *out = c;
   return 0;
 }
@@ -268,8 +304,7 @@ int ctx_set_timeout_ms(CommCtx* c, int64_t ms) {
 }
 int ctx_set_signal_pad(CommCtx* c, void* const* pads, size_t bytes) {
   if (!c || !pads) return set_error(B200_ERR_ARG, "b200_ctx_set_signal_pad: null argument");
-  if (bytes < 2 * kPadWordsPerFamily * sizeof(uint32_t))
-    return set_error(B200_ERR_ARG, "b200_ctx_set_signal_pad: %zu bytes, need %zu", bytes, 2 * kPadWordsPerFamily * sizeof(uint32_t));
+  if (bytes < kPadBytes) return set_error(B200_ERR_ARG, "b200_ctx_set_signal_pad: %zu bytes, need %zu", bytes, kPadBytes);
   for (int j = 0; j < c->world; ++j) {
     if (!pads[j]) return set_error(B200_ERR_ARG, "b200_ctx_set_signal_pad: rank %d pad is null", j);
     c->pad[j] = static_cast<uint32_t*>(pads[j]);
@@ -287,6 +322,7 @@ int ctx_register_buffer(CommCtx* c, int slot, void* const* peer_ptrs, void* mc_p
   c->buf[slot].bytes = bytes;
   return 0;
 }
+size_t ctx_signal_pad_bytes() { return kPadBytes; }
 int ctx_has_multicast(const CommCtx* c, int slot) { return c && slot >= 0 && slot < kMaxBuffers && c->buf[slot].mc != nullptr; }
 
 static int check_unit(const CommCtx* c, int slot, size_t off, int64_t n_shard, int ctas, const char* who) {
@@ -317,6 +353,24 @@ int allgather_layer(CommCtx* c, int slot, size_t off, int64_t n_shard, int mode,
   else
     all_gather_kernel<false, 4><<<ctas, 512, 0, st>>>(p, off, n_shard);
   B200_CHECK_LAUNCH("all_gather_kernel");
+  return 0;
+}
+
+// vals: n <= 16 fp32 values in this rank's device memory, replaced by their sum over all ranks (rank order, identical on every rank)
+int allreduce_scalars(CommCtx* c, float* vals, int n, cudaStream_t st) {
+  if (!c || !vals || n < 1 || n > kMaxScalars) return set_error(B200_ERR_ARG, "b200_allreduce_scalars: n %d outside 1..%d", n, kMaxScalars);
+  if (!c->pad[c->rank]) return set_error(B200_ERR_ARG, "b200_allreduce_scalars: no signal pad registered");
+  Peers p;
+  for (int j = 0; j < kMaxWorld; ++j) {
+    p.data[j] = nullptr;
+    p.pad[j] = j < c->world ? c->pad[j] : nullptr;
+  }
+  p.mc = nullptr;
+  p.rank = c->rank;
+  p.world = c->world;
+  p.timeout_ns = c->timeout_ns;
+  allreduce_scalars_kernel<<<1, 32, 0, st>>>(p, vals, n, static_cast<int>(c->scalar_calls++ & 1));
+  B200_CHECK_LAUNCH("allreduce_scalars_kernel");
   return 0;
 }
 

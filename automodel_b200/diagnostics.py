@@ -32,6 +32,8 @@ def check_collectives(eng: ShardedLlamaEngine, unit_index: int = 1, seed: int = 
     eng.g_full[ui].copy_(x)
     ref32 = x.float()
     dist.all_reduce(ref32, op=dist.ReduceOp.SUM, group=pg)           # independent path: NCCL fp32 sum of the N bf16 tensors
+    mag32 = x.float().abs()
+    dist.all_reduce(mag32, op=dist.ReduceOp.SUM, group=pg)           # sum of |addends|: the scale of fp32 accumulation error
     want = ref32[a:b].to(torch.bfloat16)
     torch.cuda.synchronize(dev)
     dist.barrier(group=pg)
@@ -43,6 +45,12 @@ def check_collectives(eng: ShardedLlamaEngine, unit_index: int = 1, seed: int = 
     got = eng.g_full[ui][a:b]
     rs_ulp = _bf16_ulp_distance(got, want)
     rs_exact = float((got == want).float().mean().item())
+    # error model of "fp32 accumulation in ANY order, then ONE rounding to bf16": |got - sum| <= 2^-8 |sum| (one bf16 ulp of the result)
+    # + 2^-21 sum|addends| (N fp32 roundings of partial sums; shows when the addends cancel).  A bf16 ring (one rounding per hop) is
+    # outside it by orders of magnitude.
+    err = (got.float() - ref32[a:b]).abs()
+    bound = ref32[a:b].abs() * 2.0 ** -8 + mag32[a:b] * 2.0 ** -21
+    rs_excess = float((err / bound.clamp_min(1e-30)).max().item())
     # a few mismatching elements of rank 0's slice with every rank's addend (how does the reducing hardware round?)
     per = (b - a)
     idx = torch.nonzero(got != want).flatten()[:4] if eng.rank == 0 else torch.zeros(0, dtype=torch.int64, device=dev)
@@ -73,11 +81,12 @@ def check_collectives(eng: ShardedLlamaEngine, unit_index: int = 1, seed: int = 
     eng.ev_ag[ui] = None
     torch.cuda.synchronize(dev)
     ag_equal = bool(torch.equal(eng.p_full[ui], want_full))
-    stats = torch.tensor([float(rs_ulp), 1.0 - rs_exact, norm_rel, 0.0 if ag_equal else 1.0], dtype=torch.float64, device=dev)
+    stats = torch.tensor([float(rs_ulp), 1.0 - rs_exact, norm_rel, 0.0 if ag_equal else 1.0, rs_excess], dtype=torch.float64, device=dev)
     dist.all_reduce(stats, op=dist.ReduceOp.MAX, group=pg)
-    rs_ulp, inexact, norm_rel, ag_bad = stats.tolist()
+    rs_ulp, inexact, norm_rel, ag_bad, rs_excess = stats.tolist()
     return {"unit_elems": int(n), "comm": eng.comm_kind, "reduce_dtype": "float32" if eng.sym is not None else eng.reduce_dtype,
             "rs_max_bf16_ulp_vs_fp32_allreduce": int(rs_ulp), "rs_frac_not_bit_equal": inexact, "rs_norm_sq_rel_err": norm_rel,
+            "rs_err_over_fp32_accumulate_bound": rs_excess,
             "ag_bit_exact": ag_bad == 0.0, "rs_mismatch_examples_rank0": examples}
 
 

@@ -839,7 +839,8 @@ class ShardedLlamaEngine:
         if fused_norm:
             self._rs_started = False
         if self.world > 1:
-            dist.all_reduce(self.norm_sq, op=dist.ReduceOp.SUM, group=self.pg)
+            if not self._sym_allreduce(self.norm_sq):
+                dist.all_reduce(self.norm_sq, op=dist.ReduceOp.SUM, group=self.pg)
         return self.norm_sq
 
     def apply_adamw(self, max_grad_norm: Optional[float] = 1.0, lr: Optional[float] = None):
@@ -901,9 +902,26 @@ class ShardedLlamaEngine:
         loss = self._allreduce_dp(self.loss_dev.clone())
         return loss[0], nsq.sqrt()[0]
 
+    def _sym_allreduce(self, t):
+        """Scalar SUM over the shard group with b200_allreduce_scalars on the communication stream (the stream of the reduce-scatter /
+        all-gather kernels: every cross-rank wait of the step then belongs to ONE sequence that is the same on all ranks, and no NCCL kernel
+        sits on the step's dependency chain).  Returns False when the symmetric-memory path does not apply."""
+        if self.sym is None or not self.streams.cuda or t.dtype != torch.float32 or t.numel() > 16 or not t.is_contiguous():
+            return False
+        st = self.streams
+        ev = st.event()
+        st.record(ev)                              # producers of `t` on the current stream
+        with torch.cuda.stream(st.comm):
+            st.wait(ev, st.comm)
+            self.ops.allreduce_scalars_(self.sym.ptr, t, stream=st.comm.cuda_stream)
+            done = st.event()
+            st.record(done, st.comm)
+        st.wait(done)
+        return True
+
     def _allreduce_dp(self, t):
         """SUM over every data-parallel rank: the shard group, then (HSDP) the replica group."""
-        if self.world > 1:
+        if self.world > 1 and not self._sym_allreduce(t):
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
         if self.replicas > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.rpg)

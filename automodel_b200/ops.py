@@ -311,3 +311,11 @@ def allgather_layer(ctx, slot, byte_offset, shard_elems, mode=0, ctas=32, stream
     check(lib().b200_allgather_layer(ctx, int(slot), int(byte_offset), int(shard_elems), int(mode), int(ctas),
                                      stream if stream is not None else _st()), "b200_allgather_layer")
     _count(1)
+
+
+def allreduce_scalars_(ctx, vals, stream=None):
+    """vals (fp32, <= 16 elements, contiguous) := sum over the ranks of the symmetric-memory context, in rank order."""
+    assert vals.dtype == torch.float32 and vals.is_contiguous() and vals.numel() <= 16
+    check(lib().b200_allreduce_scalars(ctx, vals.data_ptr(), vals.numel(), stream if stream is not None else _st()), "b200_allreduce_scalars")
+    _count(1)
+    return vals

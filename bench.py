@@ -18,6 +18,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# one hardware launch queue per stream (default 8 queues shared by every stream of the process): kernels that wait for a peer GPU
+# (the in-kernel barriers of the NVLink collectives, NCCL's) must never sit in front of unrelated work in a shared queue
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 LLAMA3_8B = {"vocab_size": 128256, "hidden_size": 4096, "intermediate_size": 14336, "num_hidden_layers": 32, "num_attention_heads": 32,
              "num_key_value_heads": 8, "max_position_embeddings": 8192, "rms_norm_eps": 1e-5, "rope_theta": 500000.0,
@@ -227,8 +230,9 @@ def main():
         col = diagnostics.check_collectives(eng, unit_index=1)
         par = diagnostics.check_sharded_step_parity(pg, dev, steps=10)
         ok = (col["ag_bit_exact"] and col["rs_norm_sq_rel_err"] < 1e-5 and par["ranks_agree"] and par["max_abs_dloss"] <= 1e-3
-              and par["max_rel_dgnorm"] <= 2e-2 and (col["reduce_dtype"] != "float32" or col["rs_max_bf16_ulp_vs_fp32_allreduce"] <= 1))
-        parity = dict(par, collectives=col, ok=bool(ok), tolerance={"max_abs_dloss": 1e-3, "max_rel_dgnorm": 2e-2, "rs_bf16_ulp": 1})
+              and par["max_rel_dgnorm"] <= 2e-2 and (col["reduce_dtype"] != "float32" or col["rs_err_over_fp32_accumulate_bound"] <= 1.0))
+        parity = dict(par, collectives=col, ok=bool(ok), tolerance={"max_abs_dloss": 1e-3, "max_rel_dgnorm": 2e-2,
+                                                          "rs": "|got - fp32 sum| <= 2^-8 |sum| + 2^-21 sum|addends| (fp32 accumulation, one rounding)"})
         if not ok:
             sys.stderr.write(f"[bench rank {rank}] N={world} parity block FAILED: {json.dumps(parity)}\n")
             if rank == 0:

@@ -144,6 +144,11 @@ int b200_ctx_register_buffer(b200_ctx* ctx, int slot, void* const* peer_ptrs, vo
 int b200_ctx_has_multicast(const b200_ctx* ctx, int slot);
 int b200_reducescatter_layer(b200_ctx* ctx, int slot, size_t byte_offset, int64_t shard_elems, int mode, int ctas, b200_stream_t stream);
 int b200_allgather_layer(b200_ctx* ctx, int slot, size_t byte_offset, int64_t shard_elems, int mode, int ctas, b200_stream_t stream);
+/* vals[0..n) (n <= 16 fp32 values in device memory) := their sum over all ranks, added in rank order on every rank (identical bits
+ * everywhere): the grad-norm^2 and reported-loss reductions of the step (components/training/utils.py:150-160 all_reduce of the norm,
+ * recipes/llm/train_ft.py:1608-1610 _dp_allreduce of the loss) without an NCCL kernel.  Same launch rules as the entries above; issue it
+ * on the same stream as them so that every cross-rank wait of the step belongs to one sequence. */
+int b200_allreduce_scalars(b200_ctx* ctx, float* vals, int n, b200_stream_t stream);
 
 #ifdef __cplusplus
 }
