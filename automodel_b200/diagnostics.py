@@ -84,7 +84,7 @@ def check_collectives(eng: ShardedLlamaEngine, unit_index: int = 1, seed: int = 
     stats = torch.tensor([float(rs_ulp), 1.0 - rs_exact, norm_rel, 0.0 if ag_equal else 1.0, rs_excess], dtype=torch.float64, device=dev)
     dist.all_reduce(stats, op=dist.ReduceOp.MAX, group=pg)
     rs_ulp, inexact, norm_rel, ag_bad, rs_excess = stats.tolist()
-    return {"unit_elems": int(n), "comm": eng.comm_kind, "reduce_dtype": "float32" if eng.sym is not None else eng.reduce_dtype,
+    return {"unit_elems": int(n), "comm": eng.comm_kind, "reduce_dtype": eng.reduce_dtype,
             "rs_max_bf16_ulp_vs_fp32_allreduce": int(rs_ulp), "rs_frac_not_bit_equal": inexact, "rs_norm_sq_rel_err": norm_rel,
             "rs_err_over_fp32_accumulate_bound": rs_excess,
             "ag_bit_exact": ag_bad == 0.0, "rs_mismatch_examples_rank0": examples}

@@ -168,10 +168,13 @@ class ShardedLlamaEngine:
         self.reduce_dtype = reduce_dtype or os.environ.get("B200_REDUCE_DTYPE", "float32")
         if self.reduce_dtype not in ("float32", "bfloat16"):
             raise ValueError(f"reduce_dtype {self.reduce_dtype!r}: float32 or bfloat16")
-        # Per-unit collectives.  "nvls": this repository's kernels on symmetric memory (b200_reducescatter_layer / b200_allgather_layer:
-        # NVSwitch multimem.ld_reduce with fp32 accumulation / multimem.st, peer loads where the platform has no multicast), always fp32
-        # accumulation; "p2p": the same entries forced onto the peer-load variant; "nccl": torch.distributed in-place collectives
-        # (multi-node / replica groups; fp32 reduction goes through an fp32 staging buffer).
+        # Per-unit collectives.  "nvls": this repository's kernels on symmetric memory (b200_allgather_layer / b200_reducescatter_layer).
+        # The all-gather is the NVSwitch multicast store (bit-exact).  The reduce-scatter follows reduce_dtype: float32 = peer loads summed
+        # in fp32 in rank order + ONE round-to-nearest-even (what the reference's fp32 reduce-scatter followed by the cast to the bf16
+        # gradient computes); bfloat16 = the NVSwitch in-fabric reduction (multimem.ld_reduce .acc::f32), measured at <= 1 bf16 ulp of the
+        # exact sum but NOT correctly rounded (ties away from zero and worse: profiles/r2_nvls_collectives.md) - the precision class of a
+        # bf16 reduction, at the lowest SM cost.  "p2p": both collectives on the peer-load variants (no multicast needed).  "nccl":
+        # torch.distributed in-place collectives (multi-node groups; fp32 reduction goes through an fp32 staging buffer).
         self.comm = comm or os.environ.get("B200_COMM", "nccl")
         if self.comm not in ("nccl", "nvls", "p2p"):
             raise ValueError(f"comm {self.comm!r}: nccl, nvls or p2p")
@@ -192,8 +195,11 @@ class ShardedLlamaEngine:
             self.sym = CommContext(process_group, dev)
             self.sym.register(CommContext.PARAMS, self._p_slab)
             self.sym.register(CommContext.GRADS, self._g_slab)
-            self._sym_mode = 1 if self.comm == "p2p" else 0
-            self.comm_kind = "nvls" if (self._sym_mode == 0 and self.sym.has_multicast(CommContext.GRADS)) else "p2p"
+            mc = self.comm == "nvls" and self.sym.has_multicast(CommContext.GRADS) and self.sym.has_multicast(CommContext.PARAMS)
+            self._ag_mode = 0 if mc else 1
+            self._rs_mode = 0 if (mc and self.reduce_dtype == "bfloat16") else 1
+            self._rs_ctas = self._comm_ctas if self._rs_mode == 0 else int(os.environ.get("B200_P2P_RS_CTAS", "64"))
+            self.comm_kind = ("nvls" if self._rs_mode == 0 else "nvls-ag+p2p-rs") if mc else "p2p"
         else:
             self.comm_kind = "nccl" if self.world > 1 else "none"
             self.p_full = [torch.zeros(u.padded, dtype=bf, device=dev) for u in self.units]   # unsharded params (shard lives inside)
@@ -404,7 +410,7 @@ class ShardedLlamaEngine:
             n_shard = self.units[ui].padded // self.world
             with torch.cuda.stream(st.comm):
                 st.wait(ev, st.comm)
-                self.ops.allgather_layer(self.sym.ptr, 0, self._unit_off[ui] * 2, n_shard, self._sym_mode, self._comm_ctas, st.comm.cuda_stream)
+                self.ops.allgather_layer(self.sym.ptr, 0, self._unit_off[ui] * 2, n_shard, self._ag_mode, self._comm_ctas, st.comm.cuda_stream)
                 done = st.event()
                 st.record(done, st.comm)
                 self.ev_ag[ui] = done
@@ -464,7 +470,7 @@ class ShardedLlamaEngine:
             with torch.cuda.stream(st.comm):
                 st.wait(ev, st.comm)
                 st.wait(wg, st.comm)
-                self.ops.reducescatter_layer(self.sym.ptr, 1, self._unit_off[ui] * 2, n_shard, self._sym_mode, self._comm_ctas, st.comm.cuda_stream)
+                self.ops.reducescatter_layer(self.sym.ptr, 1, self._unit_off[ui] * 2, n_shard, self._rs_mode, self._rs_ctas, st.comm.cuda_stream)
                 if self.replicas > 1:
                     dist.all_reduce(self.shard(self.g_full, ui), op=dist.ReduceOp.SUM, group=self.rpg)
                 self.ops.sumsq_(self.shard(self.g_full, ui), self.norm_sq, accumulate=self._rs_started)

@@ -407,7 +407,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "llama3_8b_sft_seq4096_b1_per_gpu", "layers": cfg["num_hidden_layers"], "global_batch": world, "seq_len": SEQ,
                        "parallelism": f"sharded-dp{world}", "collectives": eng.comm_kind,
-                       "grad_reduce": ("fp32 accumulate" if (eng.sym is not None or eng.reduce_dtype == "float32") else "bf16") if world > 1 else "none", "grad_accum": 1, "optimizer": "AdamW(bf16 states)" if args.adam_mode == 1 else "AdamW(fp32 math)",
+                       "grad_reduce": ("fp32 accumulate, one rounding" if eng.reduce_dtype == "float32" else "bf16") if world > 1 else "none", "grad_accum": 1, "optimizer": "AdamW(bf16 states)" if args.adam_mode == 1 else "AdamW(fp32 math)",
                        "clip_grad_norm": 1.0, "l2": "working set (16 GB params + 16 GB grads + activations) >> 126 MB L2; no flush needed",
                        "tokens_per_step": tokens_per_step},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "final_loss": final_loss, "final_grad_norm": final_gnorm,
