@@ -175,32 +175,26 @@ class ShardedLlamaEngine:
         # exact sum but NOT correctly rounded (ties away from zero and worse: profiles/r2_nvls_collectives.md) - the precision class of a
         # bf16 reduction, at the lowest SM cost.  "p2p": both collectives on the peer-load variants (no multicast needed).  "nccl":
         # torch.distributed in-place collectives (multi-node groups; fp32 reduction goes through an fp32 staging buffer).
-        self.comm = comm or os.environ.get("B200_COMM", "nccl")
-        if self.comm not in ("nccl", "nvls", "p2p"):
-            raise ValueError(f"comm {self.comm!r}: nccl, nvls or p2p")
+        # Default "auto": the symmetric-memory kernels whenever the shard group is one NVSwitch box (<= 8 CUDA ranks, no replica groups),
+        # NCCL otherwise or when the symmetric allocation / rendezvous is not available on the platform.
+        self.comm = comm or os.environ.get("B200_COMM", "auto")
+        if self.comm not in ("auto", "nccl", "nvls", "p2p"):
+            raise ValueError(f"comm {self.comm!r}: auto, nccl, nvls or p2p")
         self.sym = None
         self._comm_ctas = int(os.environ.get("B200_COMM_CTAS", "32"))
-        if self.world > 1 and dev.type == "cuda" and self.comm in ("nvls", "p2p"):
-            from .symm import SymmetricSlab, CommContext
+        want_sym = self.comm in ("nvls", "p2p") or (self.comm == "auto" and self.world <= 8 and self.replicas == 1)
+        if self.world > 1 and dev.type == "cuda" and want_sym:
             if self.world > 8:
                 raise NotImplementedError("the symmetric-memory data path spans one NVSwitch box (<= 8 ranks per shard group); use comm='nccl'")
-            offs, tot = [], 0
-            for u in self.units:
-                offs.append(tot)
-                tot += u.padded
-            self._unit_off = offs
-            self._p_slab, self._g_slab = SymmetricSlab(tot, bf, dev, process_group), SymmetricSlab(tot, bf, dev, process_group)
-            self.p_full = [self._p_slab.tensor[o:o + u.padded] for o, u in zip(offs, self.units)]
-            self.g_full = [self._g_slab.tensor[o:o + u.padded] for o, u in zip(offs, self.units)]
-            self.sym = CommContext(process_group, dev)
-            self.sym.register(CommContext.PARAMS, self._p_slab)
-            self.sym.register(CommContext.GRADS, self._g_slab)
-            mc = self.comm == "nvls" and self.sym.has_multicast(CommContext.GRADS) and self.sym.has_multicast(CommContext.PARAMS)
-            self._ag_mode = 0 if mc else 1
-            self._rs_mode = 0 if (mc and self.reduce_dtype == "bfloat16") else 1
-            self._rs_ctas = self._comm_ctas if self._rs_mode == 0 else int(os.environ.get("B200_P2P_RS_CTAS", "64"))
-            self.comm_kind = ("nvls" if self._rs_mode == 0 else "nvls-ag+p2p-rs") if mc else "p2p"
-        else:
+            try:
+                self._setup_symmetric(process_group, dev, bf)
+            except Exception as e:  # noqa: BLE001 - platform without symmetric memory / peer access
+                if self.comm != "auto":
+                    raise
+                import sys
+                sys.stderr.write(f"[automodel_b200] symmetric-memory collectives unavailable ({type(e).__name__}: {e}); using NCCL\n")
+                self.sym = None
+        if self.sym is None:
             self.comm_kind = "nccl" if self.world > 1 else "none"
             self.p_full = [torch.zeros(u.padded, dtype=bf, device=dev) for u in self.units]   # unsharded params (shard lives inside)
             self.g_full = [torch.zeros(u.padded, dtype=bf, device=dev) for u in self.units]   # unsharded grads (RS in place)
@@ -274,6 +268,27 @@ class ShardedLlamaEngine:
         self.norm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._grads_dirty = False
         self._unsynced = False    # gradients accumulated but not yet reduce-scattered (backward ran with last_micro=False)
+
+    def _setup_symmetric(self, process_group, dev, bf):
+        """Parameter and gradient storage of all units in two symmetric slabs + the b200_ctx that the collectives entries take."""
+        from .symm import SymmetricSlab, CommContext
+        offs, tot = [], 0
+        for u in self.units:
+            offs.append(tot)
+            tot += u.padded
+        self._unit_off = offs
+        self._p_slab, self._g_slab = SymmetricSlab(tot, bf, dev, process_group), SymmetricSlab(tot, bf, dev, process_group)
+        self.p_full = [self._p_slab.tensor[o:o + u.padded] for o, u in zip(offs, self.units)]
+        self.g_full = [self._g_slab.tensor[o:o + u.padded] for o, u in zip(offs, self.units)]
+        sym = CommContext(process_group, dev)
+        sym.register(CommContext.PARAMS, self._p_slab)
+        sym.register(CommContext.GRADS, self._g_slab)
+        mc = self.comm != "p2p" and sym.has_multicast(CommContext.GRADS) and sym.has_multicast(CommContext.PARAMS)
+        self._ag_mode = 0 if mc else 1
+        self._rs_mode = 0 if (mc and self.reduce_dtype == "bfloat16") else 1
+        self._rs_ctas = self._comm_ctas if self._rs_mode == 0 else int(os.environ.get("B200_P2P_RS_CTAS", "64"))
+        self.comm_kind = ("nvls" if self._rs_mode == 0 else "nvls-ag+p2p-rs") if mc else "p2p"
+        self.sym = sym
 
     # ------------------------------------------------------------------ parameter plumbing
     def _mk_fused_views(self):
