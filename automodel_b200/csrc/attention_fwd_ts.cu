@@ -131,8 +131,8 @@ attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       constexpr uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);   // O += P V   (A = P from TMEM, K = 64 kv rows, V MN-major)
       const uint32_t q_base = smem_u32(smem + L::Q_OFF);
       auto issue_s = [&](int j) {
-        // S_j overwrites the buffer that held S_{j-2} / P_{j-2}: PV_{j-2} was issued (after p_ready of tile j-2) before this call and
-        // the tensor pipe runs in issue order, so no further hand-back from the softmax warps is needed
+        // S_j overwrites the buffer that held S_{j-2} / P_{j-2}: the caller has waited for PV_{j-2} to complete, and PV_{j-2} was issued
+        // only after the softmax warps had published P_{j-2} (= finished reading S_{j-2}), so no hand-back from them is needed
         const int st = j & 1;
         mbar_wait(&k_full[st], (j >> 1) & 1);
         tc_fence_after();
@@ -147,7 +147,16 @@ attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(q_full, 0);
       issue_s(0);
       for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) issue_s(j + 1);
+        if (j + 1 < n_kv) {
+          // S_{j+1} overwrites the columns PV_{j-1} reads its A operand (P_{j-1}) from.  Issue order alone does not protect a tensor-memory
+          // A operand against the next MMA's accumulator write (seen on hardware as run-to-run differences of the 8B forward), so wait
+          // for PV_{j-1} to COMPLETE.  Off the critical path: softmax_j (the CTA's bottleneck) is still running at this point.
+          if (j > 0) {
+            mbar_wait(pv_done, (j - 1) & 1);
+            tc_fence_after();
+          }
+          issue_s(j + 1);
+        }
         const int st = j & 1;
         mbar_wait(p_ready, j & 1);
         mbar_wait(&v_full[st], (j >> 1) & 1);
@@ -324,14 +333,9 @@ int attn_fwd_ts(const void* q, const void* k, const void* v, void* o, float* lse
   if ((ldq | ldk | ldv | ldo) % 8) return set_error(B200_ERR_ARG, "attn: row pitches must be multiples of 8 elements");
   if (scale <= 0.f) return set_error(B200_ERR_ARG, "attn: scale must be positive");
 #define B200_FWDTS(DD, HH) return fwdts::launch<DD, HH>(q, k, v, o, lse, cu_seqlens, nseq, max_len, ldq, ldk, ldv, ldo, Hq, Hkv, T, scale, st)
-  if (D == 128) {
-    if (halves == 2) B200_FWDTS(128, 2);
-    B200_FWDTS(128, 1);
-  }
-  if (D == 64) {
-    if (halves == 2) B200_FWDTS(64, 2);
-    B200_FWDTS(64, 1);
-  }
+  (void)halves;   // the two-threads-per-row variant (HALVES = 2) failed its parity tests on hardware and is not instantiated
+  if (D == 128) B200_FWDTS(128, 1);
+  if (D == 64) B200_FWDTS(64, 1);
 #undef B200_FWDTS
   return set_error(B200_ERR_UNSUPPORTED, "attn: head_dim %d not in {64,128}", D);
 }

@@ -66,7 +66,7 @@ int attn_fwd_tc64(const void*, const void*, const void*, void*, float*, const in
                   int, int, float, cudaStream_t);
 int attn_fwd_ts(const void*, const void*, const void*, void*, float*, const int*, int, int, int64_t, int64_t, int64_t, int64_t, int, int,
                 int, int, float, int, cudaStream_t);
-static int g_attn_fwd_variant = 2;  // 2 (default): P kept in tensor memory, packed-fp32 softmax (attention_fwd_ts.cu, 902 TFLOP/s); 1: attention_fwd64.cu (624); 0: attention_tc.cu forward (510); 3: variant 2 with eight softmax warps per CTA
+static int g_attn_fwd_variant = 2;  // 2 (default): P kept in tensor memory, packed-fp32 softmax (attention_fwd_ts.cu, 902 TFLOP/s); 1: attention_fwd64.cu (624); 0: attention_tc.cu forward (510)
 
 // debug option: 1 (default) = tcgen05/TMEM attention, 0 = the mma.sync v1 kernels (kept for bisecting only)
 static int g_attn_impl = 1;
@@ -198,9 +198,8 @@ int b200_embed_bwd(const int* ids, const void* dh, void* dW, int* workspace, int
 int b200_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const int* cu_seqlens, int nseq, int max_seqlen,
                   int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int Hq, int Hkv, int head_dim, int total_tokens, float scale,
                   b200_stream_t stream) {
-  if (g_attn_impl == 1 && g_attn_fwd_variant >= 2)   // 2: four softmax warps per CTA; 3: eight (two threads per tile row)
-    return attn_fwd_ts(q, k, v, o, lse, cu_seqlens, nseq, max_seqlen, ldq, ldk, ldv, ldo, Hq, Hkv, head_dim, total_tokens, scale,
-                       g_attn_fwd_variant == 3 ? 2 : 1, S(stream));
+  if (g_attn_impl == 1 && g_attn_fwd_variant >= 2)
+    return attn_fwd_ts(q, k, v, o, lse, cu_seqlens, nseq, max_seqlen, ldq, ldk, ldv, ldo, Hq, Hkv, head_dim, total_tokens, scale, 1, S(stream));
   if (g_attn_impl == 1 && g_attn_fwd_variant == 1)
     return attn_fwd_tc64(q, k, v, o, lse, cu_seqlens, nseq, max_seqlen, ldq, ldk, ldv, ldo, Hq, Hkv, head_dim, total_tokens, scale, S(stream));
   if (g_attn_impl == 1)

@@ -1,6 +1,8 @@
 """Tensor-level wrappers over the C ABI.  torch supplies device memory and streams only; every op below is one or
 more launches of the hand-written sm_100a kernels in csrc/.  Inputs must be CUDA bf16 (unless noted) and contiguous
 in the last dimension."""
+import os
+
 import torch
 
 from ._lib import lib, check
@@ -297,6 +299,10 @@ def add_(dst, src):
     check(lib().b200_add_inplace_bf16(dst.data_ptr(), src.data_ptr(), dst.numel(), _st()), "b200_add_inplace_bf16")
     _count(1)
     return dst
+
+
+if os.environ.get("B200_ATTN_FWD_VARIANT"):       # A/B and bisecting knob (see include/b200_train.h b200_set_option "attn_fwd_variant")
+    set_option("attn_fwd_variant", int(os.environ["B200_ATTN_FWD_VARIANT"]))
 
 
 def reducescatter_layer(ctx, slot, byte_offset, shard_elems, mode=0, ctas=32, stream=None):

@@ -79,7 +79,7 @@ CONFIGS = {
     "qwen2_tiny_bf16": dict(gbs=2, lbs=1, steps=20, vocab=1024, hidden=256, ffn=512, layers=2, heads=4, kv=2, seq=256,
                             theta=1000000.0, dtype="bfloat16", lr="1.0e-3", opt_extra="", cfg_class="Qwen2Config", arch="Qwen2ForCausalLM", tied="true"),
     # the same model untied, fp32: the exact-math pin of the bias path for the oracle
-    "qwen2_tiny_fp32": dict(gbs=2, lbs=2, steps=3, vocab=512, hidden=128, ffn=256, layers=2, heads=2, kv=1, seq=128,
+    "qwen2_tiny_fp32": dict(gbs=2, lbs=2, steps=3, vocab=512, hidden=256, ffn=512, layers=2, heads=2, kv=1, seq=128,
                             theta=1000000.0, dtype="float32", lr="1.0e-3", opt_extra="", cfg_class="Qwen2Config", arch="Qwen2ForCausalLM", tied="false"),
 }
 

@@ -303,8 +303,7 @@ def attn_impl(request):
 DEFAULT_FWD_VARIANT = 2
 
 
-@pytest.mark.parametrize("attn_impl", [(1, 0), (1, 1), (1, 2), (1, 3), (0, 0)], indirect=True,
-                         ids=["tcgen05", "tcgen05_fwd64", "tcgen05_p_in_tmem", "p_in_tmem_8_softmax_warps", "mma_v1"])
+@pytest.mark.parametrize("attn_impl", [(1, 0), (1, 1), (1, 2), (0, 0)], indirect=True, ids=["tcgen05", "tcgen05_fwd64", "tcgen05_p_in_tmem", "mma_v1"])
 @pytest.mark.parametrize("D,Hq,Hkv", [(64, 4, 2), (128, 4, 1), (128, 2, 2)])
 @pytest.mark.parametrize("lens", [[512], [64], [1], [200, 57, 255], [130, 1, 64, 63, 65], [1024, 129, 127, 128, 300]])
 def test_attention_fwd_bwd(D, Hq, Hkv, lens, attn_impl):
@@ -332,6 +331,29 @@ def test_attention_fwd_bwd(D, Hq, Hkv, lens, attn_impl):
     for got, ref, nm in [(o, o_ref, "o"), (dq, dq_ref, "dq"), (dk, dk_ref, "dk"), (dv, dv_ref, "dv")]:
         rel = (got.float() - ref).norm() / ref.norm().clamp_min(1e-2 * math.sqrt(ref.numel()))  # len-1 sequences: dq == 0 exactly
         assert rel < 1.5e-2, (nm, rel.item())
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_attention_forward_is_bit_reproducible_at_8b_shapes(variant):
+    """S = 4096, 32/8 heads of 128: 20 launches of the forward on the same inputs give identical bits (o and lse).  Guards the
+    tensor-memory hazards of the P-in-TMEM kernel (a WAR race between PV_{j-1}'s A-operand read and S_{j+1}'s accumulator write showed up
+    only as run-to-run differences at this size, never as a tolerance failure)."""
+    ops.set_option("attn_fwd_variant", variant)
+    try:
+        T, Hq, Hkv, D = 4096, 32, 8, 128
+        g = torch.Generator(device=DEV).manual_seed(7)
+        qkv = bf(torch.randn(T, (Hq + 2 * Hkv) * D, device=DEV, generator=g))
+        cu = torch.tensor([0, T], dtype=torch.int32, device=DEV)
+        q, k, v = qkv[:, :Hq * D], qkv[:, Hq * D:(Hq + Hkv) * D], qkv[:, (Hq + Hkv) * D:]
+        o0, l0 = ops.attn_fwd(q, k, v, cu, T, Hq, Hkv, D)
+        o0, l0 = o0.clone(), l0.clone()
+        bad = 0
+        for _ in range(20):
+            o, l = ops.attn_fwd(q, k, v, cu, T, Hq, Hkv, D)
+            bad += int(not (torch.equal(o, o0) and torch.equal(l, l0)))
+        assert bad == 0, f"{bad} of 20 launches differ"
+    finally:
+        ops.set_option("attn_fwd_variant", DEFAULT_FWD_VARIANT)
 
 
 # ------------------------------------------------------------------------------------------------ cross-entropy
