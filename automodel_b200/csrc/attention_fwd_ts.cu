@@ -41,7 +41,7 @@ struct Smem {
   static constexpr int V_OFF = TILE_Q + 2 * TILE_KV;
   static constexpr int XCH_OFF = TILE_Q + 4 * TILE_KV;      // float [3][2][128]: row-max exchange (two tile parities) and final row-sum exchange
   static constexpr int BAR_OFF = XCH_OFF + 3 * 2 * 128 * 4;
-  static constexpr int NUM_BARS = 13;
+  static constexpr int NUM_BARS = 14;
   static constexpr int DYN = BAR_OFF + NUM_BARS * 8 + 16;  // 101,496 B at D=128: two CTAs per SM
 };
 
@@ -53,7 +53,7 @@ template <int D, int HALVES>
 __global__ void __launch_bounds__(64 + 128 * HALVES, 2)
 attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    __nv_bfloat16* __restrict__ o, float* __restrict__ lse, const int* __restrict__ cu_seqlens, int64_t ldo, int Hq, int Hkv, int T,
-                   float scale_log2) {
+                   float scale_log2, int throttle) {
   using L = Smem<D>;
   constexpr int ATOMS = D / 64;
   constexpr int QA = 128 * 128;  // bytes of one Q atom  [128 x 64]
@@ -67,8 +67,10 @@ attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* v_full = bars + 5;
   uint64_t* v_empty = bars + 7;
   uint64_t* s_full = bars + 9;
-  uint64_t* p_ready = bars + 11;
-  uint64_t* pv_done = bars + 12;
+  uint64_t* p_ready = bars + 11;   // [2]: one per S / P buffer.  With a single barrier a softmax warp that runs one tile ahead (the second S
+                                   // buffer lets it) would deliver its arrival for tile j+1 into the phase of tile j, completing that phase
+                                   // before a slower warp has written its rows of P_j: PV_j would read stale probabilities.
+  uint64_t* pv_done = bars + 13;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -93,7 +95,8 @@ attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
     }
-    mbar_init(p_ready, 4 * HALVES);
+    mbar_init(&p_ready[0], 4 * HALVES);
+    mbar_init(&p_ready[1], 4 * HALVES);
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
@@ -158,7 +161,7 @@ attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           issue_s(j + 1);
         }
         const int st = j & 1;
-        mbar_wait(p_ready, j & 1);
+        mbar_wait(&p_ready[st], (j >> 1) & 1);
         mbar_wait(&v_full[st], (j >> 1) & 1);
         tc_fence_after();
         const uint32_t v_base = smem_u32(smem + L::V_OFF + st * L::TILE_KV);
@@ -254,6 +257,10 @@ attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       l_sum += sa + sb;
       // P_j (bf16 pairs: CW/2 columns per thread) over the first 32 columns of S_j - every thread that reads those columns of this row
       // has done so: with HALVES == 2 the half-0 warp loaded them above and the named barrier ordered that load before this store
+      if (throttle && j > 0) {      // experiment knob: the hand-shake of the smem-P kernel (no warp publishes P_j before PV_{j-1} is done)
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+      }
       if constexpr (HALVES == 1) {
         tmem_st_32x32b_x32(tS0 + lane_addr + st * 64, pk);
       } else {
@@ -262,7 +269,7 @@ attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready);
+      if (lane == 0) mbar_arrive(&p_ready[st]);
     }
     if (HALVES == 2) {       // row sums of the two column halves (same m_used and rescale history in both)
       float* buf = xch + 2 * 256;
@@ -304,7 +311,7 @@ attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 template <int D, int HALVES>
 static int launch(const void* q, const void* k, const void* v, void* o, float* lse, const int* cu, int nseq, int max_len, int64_t ldq, int64_t ldk,
-                  int64_t ldv, int64_t ldo, int Hq, int Hkv, int T, float scale, cudaStream_t st) {
+                  int64_t ldv, int64_t ldo, int Hq, int Hkv, int T, float scale, int throttle, cudaStream_t st) {
   using L = Smem<D>;
   auto kern = attn_fwd_ts_kernel<D, HALVES>;
   static bool configured = false;
@@ -319,7 +326,7 @@ static int launch(const void* q, const void* k, const void* v, void* o, float* l
   if ((rc = make_tmap_2d_bf16(&tk, k, T, static_cast<uint64_t>(Hkv) * D, ldk, 64, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tv, v, T, static_cast<uint64_t>(Hkv) * D, ldv, 64, 64))) return rc;
   dim3 grid((max_len + 127) / 128, Hq, nseq);
-  kern<<<grid, 64 + 128 * HALVES, L::DYN, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(o), lse, cu, ldo, Hq, Hkv, T, scale * 1.4426950408889634f);
+  kern<<<grid, 64 + 128 * HALVES, L::DYN, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(o), lse, cu, ldo, Hq, Hkv, T, scale * 1.4426950408889634f, throttle);
   B200_CHECK_LAUNCH("attn_fwd_ts");
   return 0;
 }
@@ -332,8 +339,8 @@ int attn_fwd_ts(const void* q, const void* k, const void* v, void* o, float* lse
   if (Hq % Hkv) return set_error(B200_ERR_ARG, "attn: Hq %% Hkv != 0");
   if ((ldq | ldk | ldv | ldo) % 8) return set_error(B200_ERR_ARG, "attn: row pitches must be multiples of 8 elements");
   if (scale <= 0.f) return set_error(B200_ERR_ARG, "attn: scale must be positive");
-#define B200_FWDTS(DD, HH) return fwdts::launch<DD, HH>(q, k, v, o, lse, cu_seqlens, nseq, max_len, ldq, ldk, ldv, ldo, Hq, Hkv, T, scale, st)
-  (void)halves;   // the two-threads-per-row variant (HALVES = 2) failed its parity tests on hardware and is not instantiated
+#define B200_FWDTS(DD, HH) return fwdts::launch<DD, HH>(q, k, v, o, lse, cu_seqlens, nseq, max_len, ldq, ldk, ldv, ldo, Hq, Hkv, T, scale, halves == 9 ? 1 : 0, st)
+  // halves == 9: experiment knob "throttle" (attn_fwd_variant 3)   // the two-threads-per-row variant (HALVES = 2) failed its parity tests on hardware and is not instantiated
   if (D == 128) B200_FWDTS(128, 1);
   if (D == 64) B200_FWDTS(64, 1);
 #undef B200_FWDTS

@@ -300,7 +300,7 @@ def attn_impl(request):
     ops.set_option("attn_fwd_variant", DEFAULT_FWD_VARIANT)
 
 
-DEFAULT_FWD_VARIANT = 2
+DEFAULT_FWD_VARIANT = 1
 
 
 @pytest.mark.parametrize("attn_impl", [(1, 0), (1, 1), (1, 2), (0, 0)], indirect=True, ids=["tcgen05", "tcgen05_fwd64", "tcgen05_p_in_tmem", "mma_v1"])
@@ -333,7 +333,8 @@ def test_attention_fwd_bwd(D, Hq, Hkv, lens, attn_impl):
         assert rel < 1.5e-2, (nm, rel.item())
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, pytest.param(2, marks=pytest.mark.xfail(reason="open race of the opt-in P-in-TMEM forward: 1-2 of 20 launches differ", strict=False)),
+                                     pytest.param(3, marks=pytest.mark.xfail(reason="experiment: variant 2 + softmax/PV hand-shake", strict=False))])
 def test_attention_forward_is_bit_reproducible_at_8b_shapes(variant):
     """S = 4096, 32/8 heads of 128: 20 launches of the forward on the same inputs give identical bits (o and lse).  Guards the
     tensor-memory hazards of the P-in-TMEM kernel (a WAR race between PV_{j-1}'s A-operand read and S_{j+1}'s accumulator write showed up
