@@ -3,8 +3,11 @@
 // SM), with the two changes its ncu capture asked for (softmax warps issue-bound, tensor pipe 27-40 % busy):
 //   * P_j is written back with tcgen05.st INTO THE COLUMNS OF S_j (bf16 pairs: 32 of S_j's 64 columns) and O += P_j V_j takes its A
 //     operand from tensor memory (tcgen05.mma [d], [a_tmem], b_desc).  No swizzled smem tile, no fence.proxy.async, no wait for
-//     PV_{j-1} before P_j can be stored, and the S-buffer hand-back barrier disappears: the tensor pipe executes S_{j+1} after PV_{j-1}
-//     in issue order, and PV_{j-1} was issued only after the softmax warps had published P_{j-1}.
+//     S-buffer hand-back barrier (PV_{j-1} is issued only after the softmax warps have published P_{j-1}, i.e. read S_{j-1}).
+//     Three tensor-memory hazards found on hardware shape the synchronisation (all invisible to tolerance tests, caught by the
+//     bit-reproducibility test at the 8B shapes): one p_ready mbarrier per S buffer (a warp running a tile ahead must not complete
+//     the previous tile's phase), S_{j+1} is issued only after PV_{j-1} - whose A operand lives in the columns it overwrites - has
+//     COMPLETED, and no warp stores P_j while PV_{j-1} is in flight.
 //   * softmax instruction diet: row max on the raw scores with 3-input FMNMX3, exp2(s*scale - m) as ONE packed FFMA2 per two elements
 //     feeding MUFU.EX2, row sums with FADD2: 3 issue slots per element instead of 5.5.
 //   warp 0      TMA producer (Q once; K/V 64-row tiles through 2-stage rings)
@@ -53,7 +56,7 @@ template <int D, int HALVES>
 __global__ void __launch_bounds__(64 + 128 * HALVES, 2)
 attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    __nv_bfloat16* __restrict__ o, float* __restrict__ lse, const int* __restrict__ cu_seqlens, int64_t ldo, int Hq, int Hkv, int T,
-                   float scale_log2, int throttle) {
+                   float scale_log2) {
   using L = Smem<D>;
   constexpr int ATOMS = D / 64;
   constexpr int QA = 128 * 128;  // bytes of one Q atom  [128 x 64]
@@ -257,7 +260,11 @@ attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       l_sum += sa + sb;
       // P_j (bf16 pairs: CW/2 columns per thread) over the first 32 columns of S_j - every thread that reads those columns of this row
       // has done so: with HALVES == 2 the half-0 warp loaded them above and the named barrier ordered that load before this store
-      if (throttle && j > 0) {      // experiment knob: the hand-shake of the smem-P kernel (no warp publishes P_j before PV_{j-1} is done)
+      if (j > 0) {
+        // No tensor-memory store while PV_{j-1} - an MMA whose A operand is sourced from tensor memory - is in flight, even though P_j
+        // goes to other columns: without this hand-shake 4 of 300 launches at the 8B shapes came back with corrupted O rows (lse intact);
+        // with it 0 of 6000 (tools/attn_repro.py).  Free in practice: PV_{j-1} finishes ~256 clocks after p_ready(j-1), the softmax of
+        // tile j takes ~1000.
         mbar_wait(pv_done, (j - 1) & 1);
         tc_fence_after();
       }
@@ -311,7 +318,7 @@ attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 template <int D, int HALVES>
 static int launch(const void* q, const void* k, const void* v, void* o, float* lse, const int* cu, int nseq, int max_len, int64_t ldq, int64_t ldk,
-                  int64_t ldv, int64_t ldo, int Hq, int Hkv, int T, float scale, int throttle, cudaStream_t st) {
+                  int64_t ldv, int64_t ldo, int Hq, int Hkv, int T, float scale, cudaStream_t st) {
   using L = Smem<D>;
   auto kern = attn_fwd_ts_kernel<D, HALVES>;
   static bool configured = false;
@@ -326,7 +333,7 @@ static int launch(const void* q, const void* k, const void* v, void* o, float* l
   if ((rc = make_tmap_2d_bf16(&tk, k, T, static_cast<uint64_t>(Hkv) * D, ldk, 64, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tv, v, T, static_cast<uint64_t>(Hkv) * D, ldv, 64, 64))) return rc;
   dim3 grid((max_len + 127) / 128, Hq, nseq);
-  kern<<<grid, 64 + 128 * HALVES, L::DYN, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(o), lse, cu, ldo, Hq, Hkv, T, scale * 1.4426950408889634f, throttle);
+  kern<<<grid, 64 + 128 * HALVES, L::DYN, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(o), lse, cu, ldo, Hq, Hkv, T, scale * 1.4426950408889634f);
   B200_CHECK_LAUNCH("attn_fwd_ts");
   return 0;
 }
@@ -339,8 +346,8 @@ int attn_fwd_ts(const void* q, const void* k, const void* v, void* o, float* lse
   if (Hq % Hkv) return set_error(B200_ERR_ARG, "attn: Hq %% Hkv != 0");
   if ((ldq | ldk | ldv | ldo) % 8) return set_error(B200_ERR_ARG, "attn: row pitches must be multiples of 8 elements");
   if (scale <= 0.f) return set_error(B200_ERR_ARG, "attn: scale must be positive");
-#define B200_FWDTS(DD, HH) return fwdts::launch<DD, HH>(q, k, v, o, lse, cu_seqlens, nseq, max_len, ldq, ldk, ldv, ldo, Hq, Hkv, T, scale, halves == 9 ? 1 : 0, st)
-  // halves == 9: experiment knob "throttle" (attn_fwd_variant 3)   // the two-threads-per-row variant (HALVES = 2) failed its parity tests on hardware and is not instantiated
+#define B200_FWDTS(DD, HH) return fwdts::launch<DD, HH>(q, k, v, o, lse, cu_seqlens, nseq, max_len, ldq, ldk, ldv, ldo, Hq, Hkv, T, scale, st)
+  (void)halves;   // the two-threads-per-row variant (HALVES = 2) failed its parity tests on hardware and is not instantiated
   if (D == 128) B200_FWDTS(128, 1);
   if (D == 64) B200_FWDTS(64, 1);
 #undef B200_FWDTS

@@ -66,7 +66,7 @@ int attn_fwd_tc64(const void*, const void*, const void*, void*, float*, const in
                   int, int, float, cudaStream_t);
 int attn_fwd_ts(const void*, const void*, const void*, void*, float*, const int*, int, int, int64_t, int64_t, int64_t, int64_t, int, int,
                 int, int, float, int, cudaStream_t);
-static int g_attn_fwd_variant = 1;  // 1 (default): attention_fwd64.cu (624 TFLOP/s, bit-reproducible); 2: P kept in tensor memory, packed-fp32 softmax (attention_fwd_ts.cu, 860-900 TFLOP/s, all parity tests green but 1-2 of 20 launches at the 8B shapes differ in a few bits: opt-in until that race is found); 3: variant 2 + softmax/PV hand-shake (experiment); 0: attention_tc.cu forward (510)
+static int g_attn_fwd_variant = 2;  // 2 (default): P kept in tensor memory, packed-fp32 softmax (attention_fwd_ts.cu: 869 TFLOP/s, 0 of 6000 launches differ); 1: attention_fwd64.cu (627 TFLOP/s); 0: attention_tc.cu forward (510)
 
 // debug option: 1 (default) = tcgen05/TMEM attention, 0 = the mma.sync v1 kernels (kept for bisecting only)
 static int g_attn_impl = 1;
@@ -199,8 +199,7 @@ int b200_attn_fwd(const void* q, const void* k, const void* v, void* o, float* l
                   int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int Hq, int Hkv, int head_dim, int total_tokens, float scale,
                   b200_stream_t stream) {
   if (g_attn_impl == 1 && g_attn_fwd_variant >= 2)
-    return attn_fwd_ts(q, k, v, o, lse, cu_seqlens, nseq, max_seqlen, ldq, ldk, ldv, ldo, Hq, Hkv, head_dim, total_tokens, scale,
-                       g_attn_fwd_variant == 3 ? 9 : 1, S(stream));
+    return attn_fwd_ts(q, k, v, o, lse, cu_seqlens, nseq, max_seqlen, ldq, ldk, ldv, ldo, Hq, Hkv, head_dim, total_tokens, scale, 1, S(stream));
   if (g_attn_impl == 1 && g_attn_fwd_variant == 1)
     return attn_fwd_tc64(q, k, v, o, lse, cu_seqlens, nseq, max_seqlen, ldq, ldk, ldv, ldo, Hq, Hkv, head_dim, total_tokens, scale, S(stream));
   if (g_attn_impl == 1)
