@@ -105,7 +105,7 @@ class ShardedLlamaEngine:
 
     def __init__(self, cfg, device, process_group=None, max_tokens=4096, lr=1e-5, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1,
                  adam_mode=0, master_weights=False, ops=None, max_positions=None, reference_rounding=True, activation_checkpointing=False,
-                 replica_group=None, reduce_dtype=None, comm=None):
+                 replica_group=None, reduce_dtype=None, comm=None, reshard_after_forward=False):
         if ops is None:
             from . import ops as _ops  # raises if libb200_train.so is missing: no fallback
             ops = _ops
@@ -183,6 +183,10 @@ class ShardedLlamaEngine:
         self.sym = None
         self._comm_ctas = int(os.environ.get("B200_COMM_CTAS", "32"))
         want_sym = self.comm in ("nvls", "p2p") or (self.comm == "auto" and self.world <= 8 and self.replicas == 1)
+        if reshard_after_forward:
+            if self.comm in ("nvls", "p2p"):
+                raise NotImplementedError("reshard_after_forward runs on the torch.distributed collectives (comm='nccl'); the symmetric-memory pool is not built")
+            want_sym = False
         if self.world > 1 and dev.type == "cuda" and want_sym:
             if self.world > 8:
                 raise NotImplementedError("the symmetric-memory data path spans one NVSwitch box (<= 8 ranks per shard group); use comm='nccl'")
@@ -196,8 +200,17 @@ class ShardedLlamaEngine:
                 self.sym = None
         if self.sym is None:
             self.comm_kind = "nccl" if self.world > 1 else "none"
-            self.p_full = [torch.zeros(u.padded, dtype=bf, device=dev) for u in self.units]   # unsharded params (shard lives inside)
-            self.g_full = [torch.zeros(u.padded, dtype=bf, device=dev) for u in self.units]   # unsharded grads (RS in place)
+            pooled = (lambda ui: reshard_after_forward and 1 <= ui <= d.layers)      # layer units live in the reshard pool (set up below)
+            self.p_full = [None if pooled(ui) else torch.zeros(u.padded, dtype=bf, device=dev) for ui, u in enumerate(self.units)]   # unsharded params (shard lives inside)
+            self.g_full = [None if pooled(ui) else torch.zeros(u.padded, dtype=bf, device=dev) for ui, u in enumerate(self.units)]   # unsharded grads (RS in place)
+        # ---- reshard_after_forward (the reference's FSDP2 schedule, components/distributed/parallelizer.py:858-872: a decoder layer's
+        # parameters are unsharded only while the layer computes).  Persistent state of a layer unit is its 1/N parameter shard and a 1/N
+        # gradient shard; the unsharded parameters / gradients of the layers rotate through a pool of POOL buffers (all-gather before the
+        # layer's forward and again before its backward, reduce-scatter right after its backward, every micro-batch).  Memory O(P/N + POOL
+        # layers) instead of O(P): what the 70B config needs.  The embed and head units stay resident, as the reference's root unit does.
+        self.reshard = bool(reshard_after_forward)
+        if self.reshard:
+            self._setup_reshard_pool(dev, bf)
         self._rs32 = self._rs32_out = None
         if self.world > 1 and self.sym is None and self.reduce_dtype == "float32":
             big = max(u.padded for u in self.units)
@@ -290,6 +303,140 @@ class ShardedLlamaEngine:
         self.comm_kind = ("nvls" if self._rs_mode == 0 else "nvls-ag+p2p-rs") if mc else "p2p"
         self.sym = sym
 
+    # ------------------------------------------------------------------ reshard_after_forward
+    POOL = 2
+
+    def _setup_reshard_pool(self, dev, bf):
+        d, K = self.dims, self.POOL
+        L = d.layers
+        big = max(self.units[1 + l].padded for l in range(L)) if L else 0
+        self._pool_p = [torch.zeros(big, dtype=bf, device=dev) for _ in range(K)]
+        self._pool_g = [torch.zeros(big, dtype=bf, device=dev) for _ in range(K)]
+        self.p_shard, self.g_shard = [None] * len(self.units), [None] * len(self.units)
+        for ui, u in enumerate(self.units):
+            a, b = u.shard_range(self.rank, self.world)
+            if 1 <= ui <= L:
+                # the full-size buffers allocated above are dropped: layer units live as shards + pool slots
+                self.p_full[ui] = self._pool_p[(ui - 1) % K][:u.padded]
+                self.g_full[ui] = self._pool_g[(ui - 1) % K][:u.padded]
+                self.p_shard[ui] = torch.zeros(b - a, dtype=bf, device=dev)
+                self.g_shard[ui] = torch.zeros(b - a, dtype=bf, device=dev)
+            else:
+                self.p_shard[ui] = self.p_full[ui][a:b]
+                self.g_shard[ui] = self.g_full[ui][a:b]
+        self._slot_layer = [None] * K        # which layer's parameters pool slot k holds (None: stale)
+        self._slot_free = [None] * K         # event: the last compute that read parameter slot k has finished
+        self._gslot_rs = [None] * K          # event: the reduce-scatter that read gradient slot k has finished
+        self._rs_tmp = torch.zeros(big // max(self.world, 1) if big else 0, dtype=bf, device=dev)
+        self._micro = (True, True)           # (first_micro, last_micro) of the backward in progress
+
+    def _is_pooled(self, ui):
+        return self.reshard and 1 <= ui <= self.dims.layers
+
+    def _ensure_layer(self, l, prefetch_only=False):
+        """Unsharded parameters of layer l in its pool slot: copy the local shard into its place and all-gather in place (communication
+        stream on the GPU; the compute stream waits for the event unless this is a prefetch)."""
+        K = self.POOL
+        k, ui = l % K, 1 + l
+        st = self.streams
+        if self._slot_layer[k] != l:
+            u = self.units[ui]
+            a, b = u.shard_range(self.rank, self.world)
+            slot = self.p_full[ui]
+
+            def issue():
+                slot[a:b].copy_(self.p_shard[ui])
+                if self.world > 1:
+                    if st.cuda:
+                        dist.all_gather_into_tensor(slot, slot[a:b], group=self.pg)
+                    else:
+                        dist.all_gather_into_tensor(slot, slot[a:b].clone(), group=self.pg)
+
+            if st.cuda:
+                ev = st.event()
+                st.record(ev)                       # the shard (AdamW) and everything that read the slot before, as far as issued here
+                with torch.cuda.stream(st.comm):
+                    st.wait(ev, st.comm)
+                    st.wait(self._slot_free[k], st.comm)
+                    if self.ev_opt[ui] is not None:
+                        st.wait(self.ev_opt[ui], st.comm)
+                    issue()
+                    done = st.event()
+                    st.record(done, st.comm)
+                    self.ev_ag[ui] = done
+            else:
+                issue()
+            self._slot_layer[k] = l
+        if not prefetch_only and self.ev_ag[ui] is not None:
+            st.wait(self.ev_ag[ui])
+            self.ev_ag[ui] = None
+
+    def _release_layer(self, l):
+        """The compute stream is done reading layer l's parameter slot (end of its forward / backward)."""
+        if self.streams.cuda:
+            ev = self.streams.event()
+            self.streams.record(ev)
+            self._slot_free[l % self.POOL] = ev
+
+    def _reduce_scatter_pooled(self, ui):
+        """Reduce-scatter of a pooled layer unit's gradient slot into the persistent gradient shard (= on the first micro-batch, += after)."""
+        first, last = self._micro
+        st = self.streams
+        k = (ui - 1) % self.POOL
+        n = self.units[ui].padded
+        per = n // self.world
+        gslot, gsh = self.g_full[ui], self.g_shard[ui]
+        a, b = self.units[ui].shard_range(self.rank, self.world)
+        wide = self.reduce_dtype == "float32" and self.world > 1
+
+        def body():
+            if self.world == 1:
+                red = gslot[a:b]
+            elif wide:
+                g32 = gslot.float() if self._rs32 is None else self._rs32[:n].copy_(gslot)
+                o32 = torch.empty(per, dtype=torch.float32, device=gslot.device) if self._rs32_out is None else self._rs32_out[:per]
+                dist.reduce_scatter_tensor(o32, g32, op=dist.ReduceOp.SUM, group=self.pg)
+                if self.replicas > 1:
+                    dist.all_reduce(o32, op=dist.ReduceOp.SUM, group=self.rpg)
+                red = self._rs_tmp[:per].copy_(o32)
+            else:
+                red = self._rs_tmp[:per]
+                dist.reduce_scatter_tensor(red, gslot if st.cuda else gslot.clone(), op=dist.ReduceOp.SUM, group=self.pg)
+                if self.replicas > 1:
+                    dist.all_reduce(red, op=dist.ReduceOp.SUM, group=self.rpg)
+            if first:
+                gsh.copy_(red)
+            else:
+                self.ops.add_(gsh, red)
+            if last and st.cuda:      # grad-norm partial under the rest of the backward (the CPU path sums every shard in compute_grad_norm_sq)
+                self.ops.sumsq_(gsh, self.norm_sq, accumulate=self._rs_started)
+                self._rs_started = True
+
+        if st.cuda:
+            ev = st.event()
+            st.record(ev)
+            wg = self._wg_last if self._wg_on else None
+            with torch.cuda.stream(st.comm):
+                st.wait(ev, st.comm)
+                st.wait(wg, st.comm)
+                body()
+                done = st.event()
+                st.record(done, st.comm)
+                self.ev_rs[ui] = done
+                self._gslot_rs[k] = done
+        else:
+            body()
+
+    def _before_grad_slot_write(self, l):
+        """Layer l's backward is about to overwrite gradient slot l % POOL: the reduce-scatter of the layer that used it last must be done."""
+        k = l % self.POOL
+        ev = self._gslot_rs[k]
+        if ev is not None:
+            self.streams.wait(ev)
+            if self._wg_on:
+                self.streams.wait(ev, self.streams.wg)
+            self._gslot_rs[k] = None
+
     # ------------------------------------------------------------------ parameter plumbing
     def _mk_fused_views(self):
         d = self.dims
@@ -332,15 +479,21 @@ class ShardedLlamaEngine:
         if self.streams.cuda:
             torch.cuda.synchronize(self.device)
         with torch.no_grad():
-            for name, dst in self.P.items():
-                src = sd[name]
-                if isinstance(src, np.ndarray):
-                    src = torch.from_numpy(np.ascontiguousarray(src))
-                dst.copy_(src.to(dst.dtype).reshape(dst.shape))
+            for ui, u in enumerate(self.units):
+                for sl in u.slots:
+                    src, dst = sd[sl.name], self.P[sl.name]
+                    if isinstance(src, np.ndarray):
+                        src = torch.from_numpy(np.ascontiguousarray(src))
+                    if src is not dst:
+                        dst.copy_(src.to(dst.dtype).reshape(dst.shape))
+                if self._is_pooled(ui):      # the unit was assembled in its pool slot: keep this rank's shard
+                    a, b = u.shard_range(self.rank, self.world)
+                    self.p_shard[ui].copy_(self.p_full[ui][a:b])
+            if self.reshard:
+                self._slot_layer = [None] * self.POOL
             if self.master is not None:
                 for ui, u in enumerate(self.units):
-                    a, b = u.shard_range(self.rank, self.world)
-                    self.master[ui].copy_(self.p_full[ui][a:b].float())
+                    self.master[ui].copy_(self.shard(self.p_full, ui).float())
         for t in self.m + self.v:
             t.zero_()
         self.step_count = 0
@@ -384,31 +537,64 @@ class ShardedLlamaEngine:
         if self.master is not None:
             with torch.no_grad():
                 for ui, u in enumerate(self.units):
-                    a, b = u.shard_range(self.rank, self.world)
-                    self.master[ui].copy_(self.p_full[ui][a:b].float())
+                    self.master[ui].copy_(self.shard(self.p_full, ui).float())
 
     def init_random_(self, seed=0, std=0.02):
         """Random init of the metric config, on device: N(0, std) linears/embeddings, ones for norms
         (HF initialize_weights semantics, components/checkpoint/checkpointing.py:574-676).  Same values on every rank."""
         g = torch.Generator(device=self.device).manual_seed(seed)
+        self.sync_params()
         with torch.no_grad():
-            for name, p in self.P.items():
-                if name.endswith("norm.weight") or "layernorm" in name:
-                    p.fill_(1.0)
-                elif name.endswith(".bias"):
-                    p.zero_()
-                else:
-                    p.copy_((torch.randn(p.shape, generator=g, device=self.device, dtype=torch.float32) * std).to(p.dtype))
-        self.load_state_dict(self.P)
+            for ui, u in enumerate(self.units):      # unit order = the order of self.P: the same random stream as a resident engine draws
+                for sl in u.slots:
+                    name, p = sl.name, self.P[sl.name]
+                    if name.endswith("norm.weight") or "layernorm" in name:
+                        p.fill_(1.0)
+                    elif name.endswith(".bias"):
+                        p.zero_()
+                    else:
+                        p.copy_((torch.randn(p.shape, generator=g, device=self.device, dtype=torch.float32) * std).to(p.dtype))
+                if self._is_pooled(ui):
+                    a, b = u.shard_range(self.rank, self.world)
+                    self.p_shard[ui].copy_(self.p_full[ui][a:b])
+        if self.reshard:
+            self._slot_layer = [None] * self.POOL
+        self.load_state_dict(self.P) if not self.reshard else self._reset_optimizer_state()
+
+    def _reset_optimizer_state(self):
+        self.refresh_master_()
+        for t in self.m + self.v:
+            t.zero_()
+        self.step_count = 0
 
     def state_dict(self):
         self.sync_params()
-        return dict(self.P)
+        if not self.reshard:
+            return dict(self.P)
+        # reshard mode: the layers exist only as shards; gather every layer unit into a temporary (checkpoint / inspection time only)
+        out = {}
+        for ui, u in enumerate(self.units):
+            if self._is_pooled(ui):
+                full = torch.empty(u.padded, dtype=self.p_shard[ui].dtype, device=self.device)
+                if self.world > 1:
+                    dist.all_gather_into_tensor(full, self.p_shard[ui].contiguous(), group=self.pg)
+                else:
+                    full.copy_(self.p_shard[ui])
+            else:
+                full = self.p_full[ui]
+            for sl in u.slots:
+                out[sl.name] = full[sl.offset:sl.offset + sl.numel].view(sl.shape)
+        return out
 
     def named_grads(self):
         return dict(self.G)
 
     def shard(self, bufs, ui):
+        if self.reshard:
+            if bufs is self.p_full:
+                return self.p_shard[ui]
+            if bufs is self.g_full:
+                return self.g_shard[ui]
         a, b = self.units[ui].shard_range(self.rank, self.world)
         return bufs[ui][a:b]
 
@@ -526,6 +712,11 @@ class ShardedLlamaEngine:
 
     def _wait_params(self, ui):
         """Unit ui's parameters are current: its AdamW (side stream) and, with N > 1, its all-gather have completed."""
+        if self._is_pooled(ui):
+            self._ensure_layer(ui - 1)
+            if self.ev_opt[ui] is not None:      # consumed by the gather (communication stream); nothing else reads the shard here
+                self.ev_opt[ui] = None
+            return
         if self.ev_opt[ui] is not None:
             self.streams.wait(self.ev_opt[ui])
             self.ev_opt[ui] = None
@@ -559,6 +750,11 @@ class ShardedLlamaEngine:
     def sync_params(self):
         """Make the current stream wait for every pending parameter update (state_dict readers, checkpointing)."""
         for ui in range(len(self.units)):
+            if self._is_pooled(ui):      # no gather here: just order the current stream behind the shard's AdamW / a gather in flight
+                for evs in (self.ev_opt, self.ev_ag):
+                    if evs[ui] is not None:
+                        self.streams.wait(evs[ui])
+                continue
             self._wait_params(ui)
 
     # ------------------------------------------------------------------ forward + backward of one micro-batch
@@ -681,7 +877,11 @@ class ShardedLlamaEngine:
         ops.embed_fwd(ids, self.P["model.embed_tokens.weight"], out=sl(A["h"][0]))
         for l in range(L):
             self._wait_params(1 + l)
+            if self.reshard and l + 1 < L:
+                self._ensure_layer(l + 1, prefetch_only=True)     # next layer's all-gather under this layer's compute
             self._layer_forward(l, T, pos, cu, max_len)
+            if self.reshard:
+                self._release_layer(l)
         self._wait_params(1 + L)
         hL = sl(A["h"][L])
         xf = sl(self.xf)
@@ -733,16 +933,17 @@ class ShardedLlamaEngine:
 
         st = self.streams
 
-        def WG(reads, x, y, out):
+        def WG(reads, x, y, out, accumulate=None):
             """Weight-gradient GEMM out (+)= x^T y.  With the wgrad stream on it is issued there, behind an event that marks its inputs
             complete on the compute stream; `reads` names the scratch buffers it reads so their next writer can wait for it."""
+            accf = acc if accumulate is None else accumulate
             if not self._wg_on:
-                return G(ops.TN, x, y, out=out, residual=out if acc else None)
+                return G(ops.TN, x, y, out=out, residual=out if accf else None)
             ev = st.event()
             st.record(ev)
             with torch.cuda.stream(st.wg):
                 st.wait(ev, st.wg)
-                G(ops.TN, x, y, out=out, residual=out if acc else None)
+                G(ops.TN, x, y, out=out, residual=out if accf else None)
                 done = st.event()
                 st.record(done, st.wg)
             for r in reads:
@@ -758,6 +959,11 @@ class ShardedLlamaEngine:
         L, Hq, Hkv, D = d.layers, d.heads, d.kv_heads, d.head_dim
         qc, kc = d.q_cols, d.kv_cols
         acc = not first_micro
+        # reshard_after_forward: a layer's gradients are produced into a fresh pool slot and reduce-scattered every micro-batch; the
+        # accumulation over micro-batches happens on the 1/N gradient shard (the reference's FSDP2 does the same when it reshards)
+        lacc = acc and not self.reshard
+        if self.reshard:
+            self._micro = (first_micro, last_micro)
         if first_micro:
             self._rs_started = False   # a new accumulation window: grad-norm partials of an abandoned backward (no optimizer step) are dropped
         sl = lambda t: t[:T]
@@ -780,6 +986,11 @@ class ShardedLlamaEngine:
             self._reduce_scatter_unit(head_ui)
         for l in reversed(range(L)):
             W = self.W[l]
+            if self.reshard:
+                self._ensure_layer(l)                                  # unsharded parameters for the dgrad GEMMs (and the recompute)
+                if l > 0:
+                    self._ensure_layer(l - 1, prefetch_only=True)      # next layer's all-gather under this layer's backward
+                self._before_grad_slot_write(l)
             if self.recompute and l != L - 1:
                 # the shared arenas hold layer l+1 (or, for the top layer, already this layer: the forward ended there).  The previous
                 # layer's wgrad GEMMs (side stream) still read them: wait, then rebuild layer l's activations from h[l].
@@ -790,33 +1001,36 @@ class ShardedLlamaEngine:
             x2 = sl(A["x2"][l]); gu = sl(A["gu"][l]); a = sl(A["a"][l])
             da = sl(tmp["da"]); dgu = sl(tmp["dgu"]); dx = sl(tmp["dx"]); do2 = sl(tmp["do2"]); dqkv = sl(tmp["dqkv"])
             # MLP
-            WG((dh_name,), dh, a, W["d_down"])
+            WG((dh_name,), dh, a, W["d_down"], lacc)
             G(ops.NN, dh, W["down"], out=da)
             before_write("dgu")
             ops.swiglu_bwd(da, gu, out=dgu)
-            WG(("dgu",), dgu, x2, W["d_gu"])
+            WG(("dgu",), dgu, x2, W["d_gu"], lacc)
             G(ops.NN, dgu, W["gu"], out=dx)
             # dh1 = dh + rmsnorm'(dx2)
             before_write(dh_next_name)
-            ops.rmsnorm_bwd(dx, h1, W["n2"], sl(A["rstd2"][l]), dres=dh, dx=dh_next, dw=W["d_n2"], accumulate_dw=acc, workspace=self.norm_ws)
+            ops.rmsnorm_bwd(dx, h1, W["n2"], sl(A["rstd2"][l]), dres=dh, dx=dh_next, dw=W["d_n2"], accumulate_dw=lacc, workspace=self.norm_ws)
             dh, dh_next = dh_next, dh
             dh_name, dh_next_name = dh_next_name, dh_name
             # attention
-            WG((dh_name,), dh, o2, W["d_o"])
+            WG((dh_name,), dh, o2, W["d_o"], lacc)
             G(ops.NN, dh, W["o"], out=do2)
             before_write("dqkv")
             ops.attn_bwd(qkv[:, :qc], qkv[:, qc:qc + kc], qkv[:, qc + kc:], o2, do2, A["lse"][l], cu, max_len, Hq, Hkv, D,
                          dqkv[:, :qc], dqkv[:, qc:qc + kc], dqkv[:, qc + kc:], workspace=self.attn_ws)
             ops.rope_(dqkv, self.cos, self.sin, pos, Hq + Hkv, D, backward=True)
             if d.qkv_bias:
-                ops.colsum_(dqkv, W["d_qkv_b"], accumulate=acc)
-            WG(("dqkv",), dqkv, x1, W["d_qkv"])
+                ops.colsum_(dqkv, W["d_qkv_b"], accumulate=lacc)
+            WG(("dqkv",), dqkv, x1, W["d_qkv"], lacc)
             G(ops.NN, dqkv, W["qkv"], out=dx)
             before_write(dh_next_name)
-            ops.rmsnorm_bwd(dx, h, W["n1"], sl(A["rstd1"][l]), dres=dh, dx=dh_next, dw=W["d_n1"], accumulate_dw=acc, workspace=self.norm_ws)
+            ops.rmsnorm_bwd(dx, h, W["n1"], sl(A["rstd1"][l]), dres=dh, dx=dh_next, dw=W["d_n1"], accumulate_dw=lacc, workspace=self.norm_ws)
             dh, dh_next = dh_next, dh
             dh_name, dh_next_name = dh_next_name, dh_name
-            if last_micro:
+            if self.reshard:
+                self._release_layer(l)
+                self._reduce_scatter_pooled(1 + l)
+            elif last_micro:
                 self._reduce_scatter_unit(1 + l)
         if d.tied:
             st.wait(head_wg)       # the lm_head weight gradient (= or += above) is in the shared matrix; the token rows add to it
@@ -848,7 +1062,16 @@ class ShardedLlamaEngine:
             # the caller never announced the last micro-batch (recipe without the get_sync_ctx hook): the gradients of
             # every unit are complete but still local - reduce-scatter them now (correct; only the overlap with the backward is lost)
             for ui in reversed(range(nu)):
-                self._reduce_scatter_unit(ui)
+                if self._is_pooled(ui):
+                    # already reduce-scattered after every micro-batch; only the grad-norm partial of the summed shard is missing
+                    if self.ev_rs[ui] is not None:
+                        self.streams.wait(self.ev_rs[ui])
+                        self.ev_rs[ui] = None
+                    if self.streams.cuda:     # (the CPU path sums every shard below)
+                        ops.sumsq_(self.g_shard[ui], self.norm_sq, accumulate=self._rs_started)
+                        self._rs_started = True
+                else:
+                    self._reduce_scatter_unit(ui)
             self._unsynced = False
         fused_norm = self._rs_started   # the per-unit partials were already accumulated as each unit's gradients completed
         for ui in range(nu):
@@ -881,7 +1104,10 @@ class ShardedLlamaEngine:
                     ev = st.event()
                     st.record(ev)
                     self.ev_opt[ui] = ev
-                self._all_gather_unit(ui)
+                if not self._is_pooled(ui):      # pooled layers are gathered on demand, before their next forward / backward
+                    self._all_gather_unit(ui)
+            if self.reshard:
+                self._slot_layer = [None] * self.POOL      # every pool slot now holds parameters of the previous step
 
         if self.opt_overlap:
             # The HBM-bound optimizer sweep runs on its own stream, unit by unit in forward order: the next step's forward (tensor-bound)

@@ -147,3 +147,28 @@ def build_layout(d: LlamaDims, world: int) -> List[UnitLayout]:
 
 def total_params(units: List[UnitLayout]) -> int:
     return sum(u.numel for u in units)
+
+
+def memory_plan(d: LlamaDims, world: int, tokens: int, reshard_after_forward: bool = False, activation_checkpointing: bool = False,
+                master_weights: bool = False, pool: int = 2) -> dict:
+    """Bytes of HBM per rank that ShardedLlamaEngine allocates for a configuration (what its constructor sums up to; no allocation
+    here).  Used to decide between the resident layout (every unit's parameters and full-size gradients live for the whole step) and
+    reshard_after_forward (layers as 1/N shards + a `pool`-slot buffer pool), and documented for the 70B config in DESIGN.md."""
+    units = build_layout(d, world)
+    L, h, F, T = d.layers, d.hidden, d.ffn, tokens
+    padded = [u.padded for u in units]
+    layer = max(padded[1:1 + L]) if L else 0
+    root = padded[0] + padded[-1]
+    P = sum(padded)
+    if reshard_after_forward:
+        params = 2 * (root + (P - root) // world + pool * layer)
+        grads = 2 * (root + (P - root) // world + pool * layer + layer // world)
+    else:
+        params = grads = 2 * P
+    optim = (2 + 2 + (4 if master_weights else 0)) * (P // world)
+    per_layer = 2 * T * (h * 5 + d.qkv_cols + d.q_cols + 3 * F) + 4 * T * (2 + d.heads)      # x1, h1, x2, (h counted below) qkv, o2, gu (2F), a (F); rstd x2, lse
+    acts = 2 * T * h * (L + 1) + (per_layer if activation_checkpointing else per_layer * L)
+    tmp = 2 * T * (4 * h + 3 * F + d.q_cols + d.qkv_cols) + 2 * T * d.vocab + 4 * T * h    # backward scratch, logits, attention dq accumulator (fp32, Hq*D = h)
+    staging = 4 * (max(padded) + max(padded) // world) if world > 1 else 0                   # fp32 reduce staging of the NCCL path
+    total = params + grads + optim + acts + tmp + staging
+    return {"params": params, "grads": grads, "optimizer": optim, "activations": acts, "scratch_logits": tmp, "fp32_reduce_staging": staging, "total": total}

@@ -52,6 +52,7 @@ class B200ShardedConfig:
     patch_is_packed_sequence: bool = False
     mp_policy: Optional[object] = None       # MixedPrecisionPolicy: param_dtype must be bf16; reduce_dtype (float32 | bfloat16) is honoured
     reduce_dtype: Optional[str] = None       # gradient reduction precision; None = mp_policy.reduce_dtype, else float32 (FSDP2Config's default policy)
+    reshard_after_forward: bool = False      # the reference's per-layer gather/free schedule: ENGINE-LEVEL ONLY for now (see __post_init__)
     comm: Optional[str] = None               # per-unit collectives: nvls (own kernels on symmetric memory) | p2p | nccl; None = B200_COMM / default
     sequence_parallel: bool = False
     tp_plan: Optional[dict] = None
@@ -64,6 +65,10 @@ class B200ShardedConfig:
         bad += [k for k in ("tp_plan", "offload_policy", "autocast_dtype") if getattr(self, k) is not None]
         if bad:
             raise ValueError(f"strategy b200_sharded does not support {bad} (data-parallel bf16 training without offload / compile)")
+        if self.reshard_after_forward:
+            # ShardedLlamaEngine(reshard_after_forward=True) exists (layers live as shards + a 2-slot pool, verified over gloo), but the
+            # facade exposes HF-named nn.Parameters as views of resident unsharded buffers, which that mode does not have
+            raise ValueError("strategy b200_sharded: reshard_after_forward is not available through the recipe facade yet (engine-level only)")
         pd = getattr(self.mp_policy, "param_dtype", None)
         if pd is not None and pd != torch.bfloat16:
             raise ValueError(f"strategy b200_sharded computes in bf16; mp_policy.param_dtype={pd} is not supported")

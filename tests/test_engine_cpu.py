@@ -307,3 +307,83 @@ def test_unsupported_configs_are_rejected_loudly():
     with pytest.raises(ValueError):
         _rope_inv_freq(LlamaDims.from_hf(dict(base, rope_scaling={"rope_type": "yarn", "factor": 4.0})))
     LlamaDims.from_hf(dict(base, model_type="mistral", sliding_window=None))
+
+
+def _reshard_worker(rank, world, port, out_q, ga, ac):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    z, meta = load("tiny_bf16")
+    cfg = dict(model_cfg(meta), num_hidden_layers=5)     # 5 layers through a pool of 2: every slot is reused, in forward and in backward
+    oc = meta["optimizer"]
+    from oracle.portable_init import llama_param_shapes, portable_state_dict
+    params = portable_state_dict(llama_param_shapes(cfg), seed=4)
+    engs = [ShardedLlamaEngine(cfg, "cpu", process_group=dist.group.WORLD, max_tokens=meta["config"]["seq"], lr=oc["lr"], betas=tuple(oc["betas"]), eps=oc["eps"],
+                               weight_decay=oc["weight_decay"], adam_mode=1, ops=cpu_kernels, reshard_after_forward=rs, activation_checkpointing=ac) for rs in (False, True)]
+    for e in engs:
+        e.load_state_dict(params)
+    assert engs[1].p_full[1].data_ptr() == engs[1].p_full[3].data_ptr() != engs[1].p_full[2].data_ptr()     # layers share pool slots
+    res = []
+    for s in range(3):
+        mbs = []
+        for j in range(ga):
+            b = batches(z, meta, s * ga + j)[0]
+            mbs.append({"input_ids": torch.from_numpy(b["input_ids"][rank:rank + 1]), "labels": torch.from_numpy(b["labels"][rank:rank + 1])})
+        res.append([tuple(float(x) for x in e.train_step(mbs, meta["max_grad_norm"])) for e in engs])
+    sd = [e.state_dict() for e in engs]
+    dmax = max(float((sd[0][k].float() - sd[1][k].float()).abs().max()) for k in sd[0])
+    same = all(torch.equal(sd[0][k], sd[1][k]) for k in sd[0])
+    ost = [e.gather_optimizer_state() for e in engs]
+    same_opt = all(torch.equal(ost[0][k][0], ost[1][k][0]) and torch.equal(ost[0][k][1], ost[1][k][1]) for k in ost[0])
+    if rank == 0:
+        out_q.put((res, same, same_opt, dmax))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ga,ac", [(1, False), (1, True), (2, False)])
+def test_reshard_after_forward_equals_resident_parameters(ga, ac):
+    """The reference's FSDP2 schedule (parallelizer.py:858-872: layers unsharded only while they compute; all-gather before forward and
+    again before backward, reduce-scatter after each layer's backward) over gloo, world 2, 5 layers through a 2-slot pool: with one
+    micro-batch per step every loss, grad norm, weight and Adam moment equals the resident-parameter engine BIT FOR BIT (also with
+    activation checkpointing); with gradient accumulation the reduced shards are added instead of the unsharded gradients (the
+    reference does the same), which moves roundings only."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 90 + ga * 3 + int(ac)
+    procs = [ctx.Process(target=_reshard_worker, args=(r, 2, port, q, ga, ac)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res, same, same_opt, dmax = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for (l0, g0), (l1, g1) in res:
+        if ga == 1:
+            assert l0 == l1 and g0 == g1, res
+        else:
+            assert abs(l0 - l1) < 2e-4 and abs(g0 - g1) < 5e-3 * g0, res
+    if ga == 1:
+        assert same and same_opt, dmax
+    else:
+        assert dmax <= 2 * 3 * 1e-3 + 1e-3, dmax
+
+
+def test_memory_plan_70b_needs_resharding_and_checkpointing():
+    """BASELINE config 5 (Llama-3-70B, seq 8192, 8 x B200 with 180 GB): the resident layout cannot hold it, reshard_after_forward +
+    activation checkpointing can; the 8B headline config fits resident on one GPU (what bench.py runs)."""
+    from automodel_b200.layout import memory_plan
+    d70 = LlamaDims.from_hf(dict(vocab_size=128256, hidden_size=8192, intermediate_size=28672, num_hidden_layers=80, num_attention_heads=64,
+                                 num_key_value_heads=8, max_position_embeddings=8192, rms_norm_eps=1e-5, rope_theta=500000.0))
+    GB = 1e9
+    resident = memory_plan(d70, 8, 8192)
+    assert resident["params"] / GB > 140 and resident["total"] / GB > 400
+    fit = memory_plan(d70, 8, 8192, reshard_after_forward=True, activation_checkpointing=True)
+    assert fit["total"] / GB < 150, fit
+    assert fit["params"] / GB < 30 and fit["optimizer"] / GB < 40
+    no_ac = memory_plan(d70, 8, 8192, reshard_after_forward=True)
+    assert no_ac["total"] / GB > 180, no_ac          # 80 layers of saved activations at 8192 tokens do not fit without checkpointing
+    d8 = LlamaDims.from_hf(dict(vocab_size=128256, hidden_size=4096, intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32,
+                                num_key_value_heads=8, max_position_embeddings=8192, rms_norm_eps=1e-5, rope_theta=500000.0))
+    one = memory_plan(d8, 1, 4096)
+    assert 75 < one["total"] / GB < 100, one          # DESIGN.md §2: ~85 GB
