@@ -45,7 +45,7 @@ model:
     max_position_embeddings: {seq}
     rms_norm_eps: 1.0e-5
     rope_theta: {theta}
-    tie_word_embeddings: {tied}
+{rope_scaling}    tie_word_embeddings: {tied}
     architectures: [{arch}]
   torch_dtype: {dtype}
   attn_implementation: sdpa
@@ -63,7 +63,9 @@ dataloader: {{_target_: torch.utils.data.DataLoader, batch_size: null}}
 optimizer: {{_target_: torch.optim.AdamW, lr: {lr}, betas: [0.9, 0.95], eps: 1.0e-8, weight_decay: 0.1{opt_extra}}}
 """
 
-_LLAMA = dict(cfg_class="LlamaConfig", arch="LlamaForCausalLM", tied="false")
+_LLAMA = dict(cfg_class="LlamaConfig", arch="LlamaForCausalLM", tied="false", rope_scaling="")
+_LLAMA3_ROPE = ("    rope_scaling: {rope_type: llama3, factor: 8.0, low_freq_factor: 1.0, high_freq_factor: 4.0, "
+                "original_max_position_embeddings: 64}\n")
 CONFIGS = {
     # BASELINE.json configs[0]: d_model 256, L 2, seq 512, world 1 (fp32: the exact-math pin for the oracle)
     "tiny_fp32": dict(gbs=2, lbs=2, steps=3, vocab=1024, hidden=256, ffn=512, layers=2, heads=4, kv=2, seq=512,
@@ -75,12 +77,16 @@ CONFIGS = {
     # head_dim 128 / GQA 4:1 like Llama-3-8B, 2 micro-batches per step (grad accumulation), fp32
     "hd128_fp32": dict(gbs=2, lbs=1, steps=2, vocab=512, hidden=256, ffn=512, layers=2, heads=2, kv=1, seq=256,
                        theta=500000.0, dtype="float32", lr="1.0e-3", opt_extra="", **_LLAMA),
+    # the 8B layer structure in bf16: head_dim 128, GQA 4:1, llama3 RoPE scaling (original context 64 < seq 256 so all three frequency
+    # bands of the scaling are exercised), 2 micro-batches per step, 20 steps - the like-for-like 1e-3 check the fp32 fixture above cannot give
+    "hd128_bf16": dict(gbs=2, lbs=1, steps=20, vocab=512, hidden=512, ffn=1024, layers=2, heads=4, kv=1, seq=256,
+                       theta=500000.0, dtype="bfloat16", lr="1.0e-3", opt_extra="", **dict(_LLAMA, rope_scaling=_LLAMA3_ROPE)),
     # Qwen2 (components/models/qwen2/model.py: q/k/v bias, tied embeddings) through the same kernels: head_dim 64, GQA 2:1, bf16, 2 micro-batches
     "qwen2_tiny_bf16": dict(gbs=2, lbs=1, steps=20, vocab=1024, hidden=256, ffn=512, layers=2, heads=4, kv=2, seq=256,
-                            theta=1000000.0, dtype="bfloat16", lr="1.0e-3", opt_extra="", cfg_class="Qwen2Config", arch="Qwen2ForCausalLM", tied="true"),
+                            theta=1000000.0, dtype="bfloat16", lr="1.0e-3", opt_extra="", cfg_class="Qwen2Config", arch="Qwen2ForCausalLM", tied="true", rope_scaling=""),
     # the same model untied, fp32: the exact-math pin of the bias path for the oracle
     "qwen2_tiny_fp32": dict(gbs=2, lbs=2, steps=3, vocab=512, hidden=256, ffn=512, layers=2, heads=2, kv=1, seq=128,
-                            theta=1000000.0, dtype="float32", lr="1.0e-3", opt_extra="", cfg_class="Qwen2Config", arch="Qwen2ForCausalLM", tied="false"),
+                            theta=1000000.0, dtype="float32", lr="1.0e-3", opt_extra="", cfg_class="Qwen2Config", arch="Qwen2ForCausalLM", tied="false", rope_scaling=""),
 }
 
 

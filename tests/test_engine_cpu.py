@@ -38,7 +38,7 @@ def test_cu_seqlens_from_position_ids():
     assert cu.tolist() == [0, 3, 5, 6, 12] and mx == 6
 
 
-@pytest.mark.parametrize("name,prec,tol", [("tiny_bf16", "bf16", 1e-3), ("hd128_fp32", "bf16", 4e-3), ("qwen2_tiny_bf16", "bf16", 1e-3),
+@pytest.mark.parametrize("name,prec,tol", [("tiny_bf16", "bf16", 1e-3), ("hd128_fp32", "bf16", 4e-3), ("qwen2_tiny_bf16", "bf16", 1e-3), ("hd128_bf16", "bf16", 1e-3),
                                            ("qwen2_tiny_fp32", "bf16", 4e-3)])
 def test_engine_tracks_reference_fixture(name, prec, tol):
     """bf16 engine (CPU stand-in kernels) vs the reference run: loss / grad_norm per step, step-0 grads, weights."""
@@ -58,7 +58,7 @@ def test_engine_tracks_reference_fixture(name, prec, tol):
             for k, g in eng.named_grads().items():
                 # k_proj.bias: softmax is invariant to a constant added to every key, so this gradient is what RoPE's position dependence leaves
                 # of an exact zero - a sum of cancelling bf16 terms (relative noise ~10x that of the other parameters)
-                check_rel_l2(z, "grad0", k, g.float().numpy(), tol=0.15 if k.endswith("k_proj.bias") else 2e-2)
+                check_rel_l2(z, "grad0", k, g.float().numpy(), tol=0.15 if k.endswith("k_proj.bias") else (3e-2 if name == "hd128_bf16" else 2e-2))   # hd128_bf16: q/k weight grads of layer 0 sit at 2.6 % (two bf16 runs, two micro-batches)
             loss = float(eng.loss_dev[0]); gn = float(eng.optimizer_step(meta["max_grad_norm"]).sqrt())
         else:
             l, g = eng.train_step(mbs, meta["max_grad_norm"])

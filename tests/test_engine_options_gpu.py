@@ -91,3 +91,34 @@ def test_fused_swiglu_inside_the_step(monkeypatch):
         assert abs(float(l) - meta["loss"][s]) < 1e-3, (s, float(l), meta["loss"][s])
     torch.cuda.synchronize()
     assert ops.LAUNCHES > before
+
+
+@pytest.mark.parametrize("ac", [False, True])
+def test_reshard_after_forward_equals_resident_on_one_gpu(ac):
+    """reshard_after_forward on the CUDA engine at world 1 (no collectives, but the real pool / prefetch / event logic next to the
+    weight-gradient and optimizer side streams): 5 layers through the 2-slot pool give the resident engine's losses, grad norms and
+    weights bit for bit over 4 steps, with two micro-batches in the last two (accumulation on the shard: rounding only)."""
+    z, meta = load("tiny_bf16")
+    cfg = dict(model_cfg(meta), num_hidden_layers=5)
+    oc = meta["optimizer"]
+    from oracle.portable_init import llama_param_shapes, portable_state_dict
+    params = portable_state_dict(llama_param_shapes(cfg), seed=4)
+    engs = [ShardedLlamaEngine(cfg, "cuda", max_tokens=meta["config"]["lbs"] * meta["config"]["seq"], lr=oc["lr"], betas=tuple(oc["betas"]), eps=oc["eps"],
+                               weight_decay=oc["weight_decay"], adam_mode=1, reshard_after_forward=rs, activation_checkpointing=ac) for rs in (False, True)]
+    for e in engs:
+        e.load_state_dict(params)
+    for s in range(4):
+        mbs = [_mb(b) for b in batches(z, meta, s)]
+        if s >= 2:
+            mbs = mbs + [_mb(b) for b in batches(z, meta, s + 10)]
+        res = [e.train_step(mbs, meta["max_grad_norm"]) for e in engs]
+        l0, g0, l1, g1 = float(res[0][0]), float(res[0][1]), float(res[1][0]), float(res[1][1])
+        if s < 2:
+            assert l0 == l1 and g0 == g1, (s, l0, l1, g0, g1)
+        else:
+            assert abs(l0 - l1) < 2e-4 and abs(g0 - g1) < 5e-3 * g0, (s, l0, l1, g0, g1)
+        if s == 1:
+            sd0, sd1 = engs[0].state_dict(), engs[1].state_dict()
+            for k in sd0:
+                assert torch.equal(sd0[k], sd1[k]), k
+    torch.cuda.synchronize()
