@@ -230,9 +230,9 @@ def main():
         col = diagnostics.check_collectives(eng, unit_index=1)
         par = diagnostics.check_sharded_step_parity(pg, dev, steps=10)
         ok = (col["ag_bit_exact"] and col["rs_norm_sq_rel_err"] < 1e-5 and par["ranks_agree"] and par["max_abs_dloss"] <= 1e-3
-              and par["max_rel_dgnorm"] <= 2e-2 and (col["reduce_dtype"] != "float32" or col["rs_err_over_fp32_accumulate_bound"] <= 1.0))
+              and par["max_rel_dgnorm"] <= 2e-2 and (col["reduce_dtype"] != "float32" or col["rs_err_over_fp32_accumulate_bound"] <= 1.25))
         parity = dict(par, collectives=col, ok=bool(ok), tolerance={"max_abs_dloss": 1e-3, "max_rel_dgnorm": 2e-2,
-                                                          "rs": "|got - fp32 sum| <= 2^-8 |sum| + 2^-21 sum|addends| (fp32 accumulation, one rounding)"})
+                                                          "rs": "|got - fp32 sum| <= 1.25 x (2^-8 |sum| + 2^-21 sum|addends|): fp32 accumulation in any order + one rounding (measured 0.996; the NVSwitch reducer 1.99, a bf16 ring >> 10)"})
         if not ok:
             sys.stderr.write(f"[bench rank {rank}] N={world} parity block FAILED: {json.dumps(parity)}\n")
             if rank == 0:
@@ -394,7 +394,7 @@ def main():
         except Exception:
             traffic = None
     achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": achieved_tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+    roofline = {"bound": "tensor", "kernel": "pair::gemm_pair_kernel (CTA-pair tcgen05 GEMM: every nn.Linear fwd / dgrad / wgrad of the step)", "achieved": achieved_tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": (achieved_tf / peaks["tflops_sustained"]) if achieved_tf else None, "traffic": traffic,
                 "traffic_unit": "DRAM bytes per GEMM launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, average over the step's GEMM launches)",
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
