@@ -208,3 +208,25 @@ def test_strategy_config_accepts_an_fsdp2_yaml_and_refuses_what_it_cannot_honour
     for bad in (dict(sequence_parallel=True), dict(enable_compile=True), dict(tp_plan={"a": 1}), dict(offload_policy=object())):
         with pytest.raises(ValueError):
             B200ShardedConfig(**bad)
+
+
+def test_reduce_dtype_is_honoured_or_refused():
+    """FSDP2Config's default MixedPrecisionPolicy reduces gradients in fp32 (components/distributed/config.py:121-132).  The strategy
+    config maps `mp_policy.reduce_dtype` / `reduce_dtype` onto the engine's reduction kind (round 1 silently reduced in bf16) and refuses
+    what it cannot do."""
+    from torch.distributed.fsdp import MixedPrecisionPolicy
+    assert B200ShardedConfig().reduce_dtype == "float32"
+    assert B200ShardedConfig(mp_policy=MixedPrecisionPolicy(param_dtype=torch.bfloat16, reduce_dtype=torch.float32)).reduce_dtype == "float32"
+    assert B200ShardedConfig(mp_policy=MixedPrecisionPolicy(param_dtype=torch.bfloat16, reduce_dtype=torch.bfloat16)).reduce_dtype == "bfloat16"
+    assert B200ShardedConfig(reduce_dtype="bf16").reduce_dtype == "bfloat16"
+    assert B200ShardedConfig(mp_policy=MixedPrecisionPolicy(reduce_dtype=torch.float32), reduce_dtype="bfloat16").reduce_dtype == "bfloat16"   # explicit key wins
+    for bad in (dict(reduce_dtype="float16"), dict(mp_policy=MixedPrecisionPolicy(reduce_dtype=torch.float16)),
+                dict(mp_policy=MixedPrecisionPolicy(param_dtype=torch.float32)), dict(mp_policy=MixedPrecisionPolicy(output_dtype=torch.float32)),
+                dict(reshard_after_forward=True)):
+        with pytest.raises(ValueError):
+            B200ShardedConfig(**bad)
+    z, meta = load("hd128_fp32")
+    for rd in ("float32", "bfloat16"):
+        mgr = B200ShardedManager(B200ShardedConfig(max_tokens=meta["config"]["seq"], reduce_dtype=rd, comm="nccl"), device=torch.device("cpu"), ops=cpu_kernels)
+        model = mgr.parallelize(_Cfg(model_cfg(meta)))
+        assert model.engine.reduce_dtype == rd and model.engine.comm == "nccl"
