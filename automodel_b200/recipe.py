@@ -453,6 +453,11 @@ class B200ShardedManager:
             expected = {sl.name for u in build_layout(LlamaDims.from_hf(cfg_d), 1) for sl in u.slots}
             names = {n for n, _ in model.named_parameters()}
             extra, missing = sorted(names - expected), sorted(expected - names)
+            if cfg_d.get("tie_word_embeddings") and extra == ["lm_head.weight"]:
+                # the config ties lm_head to the embedding but the module handed over still lists a separate lm_head parameter (meta-device
+                # builds before tie_weights(), or a transformers version whose tie_weights() does not act on the reference's custom class):
+                # the engine follows the CONFIG - one shared matrix, as the reference does after loading (checkpointing.py:720-722)
+                extra = []
             if extra or missing:
                 raise NotImplementedError(f"strategy b200_sharded: the model's parameters are not the Llama set the engine implements "
                                           f"(unexpected {extra[:3]}, missing {missing[:3]}); PEFT adapters / other architectures are not supported")

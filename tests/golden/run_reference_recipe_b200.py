@@ -100,7 +100,7 @@ def main(name, loss_kind, steps):
     z, meta = load(name)
     # what the recipe's own initialisation left in the flat buffers (from_config: Checkpointer.initialize_model_weights, before or after
     # sharding depending on the world size)
-    init_fp = [float(sum(p.double().abs().sum() for p in model.engine.p_full)), float(min(float(p.float().abs().max()) for p in model.engine.P.values()))]
+    init_fp = [float(sum(p.double().abs().sum() for p in model.engine.p_full)), float(min(float(p.float().abs().max()) for n_, p in model.engine.P.items() if not n_.endswith(".bias")))]     # (HF zero-initialises biases)
     if pre:
         from safetensors.torch import load_file
         want = {}

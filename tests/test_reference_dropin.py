@@ -53,7 +53,8 @@ def _run_world(world, name, loss_kind, steps, **extra_env):
     return recs
 
 
-@pytest.mark.parametrize("name,loss_kind,steps,loss_tol", [("hd128_fp32", "reference_loss", 2, 4e-3), ("tiny_bf16", "fused_loss", 8, 1e-3)])
+@pytest.mark.parametrize("name,loss_kind,steps,loss_tol", [("hd128_fp32", "reference_loss", 2, 4e-3), ("tiny_bf16", "fused_loss", 8, 1e-3),
+                                                          ("qwen2_tiny_fp32", "reference_loss", 3, 4e-3), ("qwen2_tiny_bf16", "fused_loss", 8, 1e-3)])
 def test_reference_recipe_trains_through_b200_strategy(name, loss_kind, steps, loss_tol):
     """Training curve vs the FSDP2 fixture; the fused-loss run also goes through the recipe's validation loop after every step
     (model.eval(), is_train=False, loss_fn called with num_label_tokens=None = plain sum)."""
