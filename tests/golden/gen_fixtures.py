@@ -84,6 +84,11 @@ CONFIGS = {
     # Qwen2 (components/models/qwen2/model.py: q/k/v bias, tied embeddings) through the same kernels: head_dim 64, GQA 2:1, bf16, 2 micro-batches
     "qwen2_tiny_bf16": dict(gbs=2, lbs=1, steps=20, vocab=1024, hidden=256, ffn=512, layers=2, heads=4, kv=2, seq=256,
                             theta=1000000.0, dtype="bfloat16", lr="1.0e-3", opt_extra="", cfg_class="Qwen2Config", arch="Qwen2ForCausalLM", tied="true", rope_scaling=""),
+    # Mistral (HF MistralForCausalLM: the reference has no custom class for it) without sliding window: Llama parameter set, HF's RMSNorm
+    # (weight multiply AFTER the down-cast) - a third family through the same kernels
+    "mistral_tiny_bf16": dict(gbs=2, lbs=2, steps=20, vocab=1024, hidden=256, ffn=512, layers=2, heads=4, kv=2, seq=256,
+                              theta=10000.0, dtype="bfloat16", lr="1.0e-3", opt_extra="", cfg_class="MistralConfig", arch="MistralForCausalLM", tied="false",
+                              rope_scaling="    sliding_window: null\n"),
     # the same model untied, fp32: the exact-math pin of the bias path for the oracle
     "qwen2_tiny_fp32": dict(gbs=2, lbs=2, steps=3, vocab=512, hidden=256, ffn=512, layers=2, heads=2, kv=1, seq=128,
                             theta=1000000.0, dtype="float32", lr="1.0e-3", opt_extra="", cfg_class="Qwen2Config", arch="Qwen2ForCausalLM", tied="false", rope_scaling=""),

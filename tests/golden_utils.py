@@ -23,6 +23,8 @@ def model_cfg(meta):
     }
     if "llama3" in (c.get("rope_scaling") or ""):
         out["rope_scaling"] = {"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0, "original_max_position_embeddings": 64}
+    if c.get("cfg_class") == "MistralConfig":
+        out.update(model_type="mistral", sliding_window=None)
     if c.get("cfg_class") == "Qwen2Config":
         out.update(model_type="qwen2", tie_word_embeddings=c.get("tied") == "true")
     return out

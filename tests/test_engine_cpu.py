@@ -38,7 +38,7 @@ def test_cu_seqlens_from_position_ids():
     assert cu.tolist() == [0, 3, 5, 6, 12] and mx == 6
 
 
-@pytest.mark.parametrize("name,prec,tol", [("tiny_bf16", "bf16", 1e-3), ("hd128_fp32", "bf16", 4e-3), ("qwen2_tiny_bf16", "bf16", 1e-3), ("hd128_bf16", "bf16", 1e-3),
+@pytest.mark.parametrize("name,prec,tol", [("tiny_bf16", "bf16", 1e-3), ("hd128_fp32", "bf16", 4e-3), ("qwen2_tiny_bf16", "bf16", 1e-3), ("hd128_bf16", "bf16", 1e-3), ("mistral_tiny_bf16", "bf16", 1e-3),
                                            ("qwen2_tiny_fp32", "bf16", 4e-3)])
 def test_engine_tracks_reference_fixture(name, prec, tol):
     """bf16 engine (CPU stand-in kernels) vs the reference run: loss / grad_norm per step, step-0 grads, weights."""
